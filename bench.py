@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the molearn physics hot path on B200 (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): conformations/s, energy + gradient of all four TorchProteinEnergy terms
+(bond, angle, torsion, soft non-bonded), MurD backbone+CB (N = 2145), batch 64, FP32.
+One "step" = one batch of 64 conformations through the hot path.
+
+  value     device-resident inputs, C-ABI call (mlp_energy_eval: energies + dE/dx), CUDA events
+  e2e       the public Python API (TorchProteinEnergy.energy_per_conformation + backward) with
+            pinned HOST buffers: H2D of the batch, D2H of energies and gradient inside the timing
+  roofline  the dominant kernel (non-bonded pair kernel) against the FP32 FMA peak, plus the
+            bonded kernel against the measured HBM bandwidth at a large batch (roofline_bonded)
+  cpu_baseline / --impl reference
+            the PyTorch CPU port of the reference algorithm (oracle/torch_port.py) on the host
+            cores, on a bounded sample (8 of the 64 conformations)
+
+N > 1 (torchrun): the loss path is "replicas only"  - every rank runs its own batch
+of 64, value = total conformations / max-over-ranks time ("weak").  The latent-grid scan, which
+does shard, is reported in the "scan" object.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "conformations/sec energy+grad (MurD, batch 64)"
+UNIT = "conformations/s"
+B = 64
+ATOMS = ("N", "CA", "CB", "C", "O")
+FLOPS_PER_PAIR = 31          # FMA = 2, MUFU not counted, fast path
+CPU_SAMPLE = 8
+
+
+# ---------------------------------------------------------------------------------------------
+def murd():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "murd_input.npz"))
+    keep = np.isin(d["names"], ATOMS)
+    info = np.empty((int(keep.sum()), 3), dtype=object)
+    info[:, 0] = [str(s) for s in d["names"][keep]]
+    info[:, 1] = [str(s) for s in d["resnames"][keep]]
+    info[:, 2] = [int(r) for r in d["resids"][keep]]
+    return info, np.ascontiguousarray(d["coords"][:, keep])          # [16,N,3] Angstrom
+
+
+def make_batch(frames, seed, batch=B):
+    """SURVEY 8d config 2 input: the 16 test frames tiled + N(0, 0.1 A) noise, seeded."""
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.arange(batch) % frames.shape[0]
+    x = torch.from_numpy(frames)[idx] + 0.1 * torch.randn(batch, frames.shape[1], 3, generator=g)
+    return x.float().contiguous()                                      # [B,N,3]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for l in self.lines:
+            p = [s.strip() for s in l.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_port_rate(topo_dict, x_bn3, reps, warm=1):
+    """conformations/s of the PyTorch CPU port (fwd + bwd, all four terms), all host threads."""
+    from oracle.torch_port import TorchCPUPort
+    torch.set_num_threads(os.cpu_count() or 1)
+    port = TorchCPUPort(topo_dict)
+    x = x_bn3.permute(0, 2, 1).contiguous()
+    for _ in range(warm):
+        port.energy_and_grad(x)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        port.energy_and_grad(x)
+        ts.append(time.perf_counter() - t0)
+    return x.shape[0] / float(np.median(ts)), float(np.median(ts)), torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm's CPU path (PyTorch port), bounded sample per step."""
+    if rank != 0:
+        return
+    from molearn_b200 import Topology
+    info, frames = murd()
+    topo = Topology(info).as_dict()
+    x = make_batch(frames, 0)[:CPU_SAMPLE]
+    from oracle.torch_port import TorchCPUPort
+    torch.set_num_threads(os.cpu_count() or 1)
+    port = TorchCPUPort(topo)
+    xx = x.permute(0, 2, 1).contiguous()
+    for _ in range(args.warmup):
+        port.energy_and_grad(xx)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        port.energy_and_grad(xx)
+    dt = time.perf_counter() - t0
+    value = CPU_SAMPLE * args.steps / dt
+    sample = f"{CPU_SAMPLE} of the {B} conformations per step (fwd+bwd, 4 terms)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(len(info)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_atoms):
+    return {"workload": f"MurD backbone+CB (N={n_atoms}) TorchProteinEnergy bond+angle+torsion+soft-NB energy and dE/dx, batch {B}",
+            "batch": B, "n_atoms": n_atoms, "terms": "bond,angle,torsion,nb(repulsive)",
+            "l2": "inputs/outputs rotate through a pool of batches larger than the 126 MB L2",
+            "parallelism": "replicas (one batch per GPU, no data-path collective)"}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline_bonded / large-N extras")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    import torch.distributed as dist
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from molearn_b200 import TorchProteinEnergy, _lib
+    info, frames = murd()
+    tpe = TorchProteinEnergy(None, info, device=dev)
+    top = tpe.topology
+    N = top.n_atoms
+    dv = tpe._dev()
+    pk, pk_kind = peaks()
+
+    # pool of distinct batches > L2 (126 MB): P * 64 * N * 12 B
+    per = B * N * 12
+    P = max(8, int(np.ceil(160e6 / per)))
+    xs = torch.stack([make_batch(frames, 1000 * rank + i) for i in range(P)]).to(dev)     # [P,B,N,3]
+    gs = torch.empty_like(xs)
+    en = torch.empty((P, B, 4), device=dev)
+
+    def step(i):
+        k = i % P
+        dv.eval(xs[k].permute(0, 2, 1), en[k], gs[k].permute(0, 2, 1), None, _lib.TERM_ALL)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warm + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = dv.launches
+    ms = timed(step, args.steps, args.warmup)
+    launches = dv.launches - l0 - 0
+    launches = launches * args.steps // (args.steps + args.warmup)
+    clk = clocks.stop()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region -------------
+    hx = [make_batch(frames, 5000 + 1000 * rank + i).pin_memory() for i in range(8)]
+    hg = torch.empty((B, N, 3)).pin_memory()
+    he = torch.empty((B, 4)).pin_memory()
+    dx = torch.empty((B, N, 3), device=dev)
+
+    def e2e_step(i):
+        dx.copy_(hx[i % len(hx)], non_blocking=True)
+        x = dx.permute(0, 2, 1).detach().requires_grad_(True)
+        e = tpe.energy_per_conformation(x)
+        e.sum().backward()
+        he.copy_(e.detach(), non_blocking=True)
+        hg.copy_(x.grad.permute(0, 2, 1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()                       # the caller reads the result
+
+    e2e_steps = max(10, args.steps // 4)
+    ms_e2e = timed(e2e_step, e2e_steps, 3)
+    e2e = {"value": world * B * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": per, "d2h_bytes_per_step": per + B * 16, "ms_per_step": ms_e2e / e2e_steps}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(N), "clocks": clk, "e2e": e2e,
+        "gpu_launches": int(launches),
+    }
+
+    if rank == 0:
+        # ---- per-kernel durations (CUDA events on the launching stream, inside the C ABI) ----
+        dv.profile(True)
+        for i in range(args.steps):
+            step(i)
+        prof = dv.profile_read()
+        dv.profile(False)
+        nb_ms = prof["nb"][0] / max(prof["nb"][1], 1)
+        bd_ms = prof["bonded"][0] / max(prof["bonded"][1], 1)
+        pack_ms = prof["nb_pack"][0] / max(prof["nb_pack"][1], 1)
+        fp32_peak = 148 * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12       # TFLOP/s, FMA pipe
+        flops = FLOPS_PER_PAIR * top.n_nb_pairs * B
+        ach = flops / (nb_ms * 1e-3) / 1e12
+        out["roofline"] = {"kernel": "nb_kernel<grad>", "bound": "fp32", "achieved": ach, "peak": fp32_peak,
+                           "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
+                           "peak_source": "148 SM x 128 FMA lanes x 2 x sm_max_mhz (FP32 pipe; no tensor cores on this path)",
+                           "algorithmic_flops_per_launch": flops, "kernel_ms": nb_ms,
+                           "share_of_step": nb_ms / (ms / args.steps),
+                           "other_kernels_ms": {"bonded": bd_ms, "nb_pack": pack_ms}}
+        if not args.no_extras:
+            # bonded kernel against HBM at a batch that is not launch-latency bound
+            BB = 4096
+            xb = make_batch(frames, 77, 64).to(dev).repeat(BB // 64, 1, 1)
+            xb += 0.01 * torch.randn_like(xb)
+            gb = torch.empty_like(xb)
+            eb = torch.empty((BB, 4), device=dev)
+            dv.profile(True)
+            for _ in range(13):
+                dv.eval(xb.permute(0, 2, 1), eb, gb.permute(0, 2, 1), None, _lib.TERM_BONDED)
+            pr = dv.profile_read()
+            dv.profile(False)
+            t_ms = pr["bonded"][0] / pr["bonded"][1]
+            topo_bytes = len(top.bond_idxs) * 16 + len(top.angle_idxs) * 32 + len(top.torsion_idxs) * 64
+            byts = 24 * N * BB + topo_bytes
+            gbs = byts / (t_ms * 1e-3) / 1e9
+            out["roofline_bonded"] = {"kernel": "bonded_kernel<grad>", "bound": "hbm", "batch": BB, "achieved": gbs,
+                                      "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                      "traffic": None, "algorithmic_bytes_per_launch": byts, "kernel_ms": t_ms,
+                                      "conformations_per_s": BB / (t_ms * 1e-3)}
+            del xb, gb, eb
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, cores = cpu_port_rate(top.as_dict(), make_batch(frames, 0)[:CPU_SAMPLE], reps=5)
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{CPU_SAMPLE} of the {B} conformations, fwd+bwd of all four terms, "
+                                             f"median of 5 ({sec:.3f} s each), PyTorch CPU port of the reference (roll + cdist)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path, called through the drop-in Python class -> ctypes -> C ABI,
+against (a) the committed fp64 outputs of the unmodified reference and (b) the pinned fp64 oracle
+on seeded inputs.  Tolerance (north_star): 1e-5 relative, per term, energies and gradients."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import atominfo_from, rel
+from oracle import energy_oracle as eo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+TERMS = ("bond", "angle", "torsion", "nb")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def energy_objs(dev, golden_topo):
+    from molearn_b200 import TorchProteinEnergy
+    cache = {}
+
+    def get(case, NB="repulsive"):
+        if (case, NB) not in cache:
+            cache[(case, NB)] = TorchProteinEnergy(None, atominfo_from(golden_topo(case)), device=dev, NB=NB)
+        return cache[(case, NB)]
+    return get
+
+
+def per_term_grads(tpe, x):
+    """[4,B,N,3] gradient of each term's batch sum, through autograd (exercises the weighted backward)."""
+    out = []
+    for k in range(4):
+        xx = x.clone().requires_grad_(True)
+        e = tpe.energy_per_conformation(xx)
+        (g,) = torch.autograd.grad(e[:, k].sum(), xx)
+        out.append(g.permute(0, 2, 1).double().cpu().numpy())
+    return np.stack(out)
+
+
+def test_energies_and_gradients_vs_reference(case, dev, energy_objs, golden_energy):
+    en = golden_energy(case)
+    tpe = energy_objs(case)
+    x = torch.from_numpy(en["x"]).to(dev).permute(0, 2, 1)         # [B,3,N] view of [B,N,3] storage
+    e = tpe.energy_per_conformation(x).double().cpu().numpy()
+    for k, name in enumerate(TERMS):
+        err = np.abs(e[:, k] - en["e64"][:, k]) / np.abs(en["e64"][:, k])
+        assert err.max() < TOL, (name, err)
+    gf = list(en["grad_frames"])
+    g = per_term_grads(tpe, x[gf])
+    for k, name in enumerate(TERMS):
+        for q in range(len(gf)):
+            assert rel(g[k, q], en["g64"][q, k]) < TOL, (name, gf[q], rel(g[k, q], en["g64"][q, k]))
+
+
+def test_reference_api_conventions(dev, energy_objs, golden_energy):
+    """get_energy: bonded batch means + NB batch sum; _roll_...: batch sums (SURVEY E-4)."""
+    en = golden_energy("bbcb")
+    tpe = energy_objs("bbcb")
+    x = torch.from_numpy(en["x"][:8]).to(dev).permute(0, 2, 1).contiguous()   # reference layout [B,3,N]
+    s = en["e64"][:8].sum(0)
+    b, a, t, nb = (float(v) for v in tpe.get_energy(x, nonbonded=True))
+    assert abs(b - s[0] / 8) < TOL * s[0] / 8 and abs(a - s[1] / 8) < TOL * s[1] / 8
+    assert abs(t - s[2] / 8) < TOL * s[2] / 8 and abs(nb - s[3]) < TOL * abs(s[3])
+    assert len(tpe.get_energy(x)) == 3
+    bs, as_, ts = (float(v) for v in tpe._roll_bond_angle_torsion_loss(x))
+    assert abs(bs - s[0]) < TOL * s[0] and abs(as_ - s[1]) < TOL * s[1] and abs(ts - s[2]) < TOL * s[2]
+    assert abs(float(tpe._nb_loss(x)) - s[3]) < TOL * abs(s[3])
+    assert abs(float(tpe._conv_bond_loss(x)) - s[0]) < TOL * s[0]
+    # known answers of SURVEY 8c (frames 0-7, fp32 reference run)
+    assert abs(b - 812.5279) < 2e-2 and abs(a - 712.2919) < 2e-2 and abs(t - 2845.1143) < 5e-2
+
+
+def test_total_gradient_one_backward(dev, energy_objs, golden_energy):
+    """loss = sum of all four terms: the fused forward gradient, one backward."""
+    en = golden_energy("bbcb")
+    tpe = energy_objs("bbcb")
+    gf = list(en["grad_frames"])
+    x = torch.from_numpy(en["x"][gf]).to(dev).permute(0, 2, 1).contiguous().requires_grad_(True)
+    b, a, t, nb = tpe.get_energy(x, nonbonded=True)
+    (b * len(gf) + a * len(gf) + t * len(gf) + nb).backward()
+    want = en["g64"].sum(1)
+    got = x.grad.permute(0, 2, 1).double().cpu().numpy()
+    for q in range(len(gf)):
+        assert rel(got[q], want[q]) < TOL
+
+
+def test_weighted_backward(dev, energy_objs, golden_energy):
+    """Arbitrary upstream weights per conformation and per term."""
+    en = golden_energy("bbcb")
+    tpe = energy_objs("bbcb")
+    gf = list(en["grad_frames"])
+    w = torch.tensor([[1.0, -2.0, 0.5, 3.0], [0.0, 1.0, 1.0, 1.0], [2.0, 2.0, 2.0, 2.0], [0.3, 0.0, 0.0, -1.0],
+                      [1.0, 1.0, 1.0, 0.0]], device=dev)
+    x = torch.from_numpy(en["x"][gf]).to(dev).permute(0, 2, 1).requires_grad_(True)
+    e = tpe.energy_per_conformation(x)
+    (e * w).sum().backward()
+    got = x.grad.permute(0, 2, 1).double().cpu().numpy()
+    wn = w.double().cpu().numpy()
+    for q in range(len(gf)):
+        want = sum(wn[q, k] * en["g64"][q, k] for k in range(4))
+        scale = sum(abs(wn[q, k]) * np.linalg.norm(en["g64"][q, k]) for k in range(4))
+        assert np.linalg.norm(got[q] - want) < TOL * scale
+
+
+def test_layouts_agree(dev, energy_objs, golden_energy):
+    """[B,3,N] contiguous, permuted [B,N,3] storage, and a decoder-like padded slice."""
+    en = golden_energy("bbcb")
+    tpe = energy_objs("bbcb")
+    xn = torch.from_numpy(en["x"][[0, 9, 12]]).to(dev)              # [B,N,3]
+    B, N, _ = xn.shape
+    a = xn.permute(0, 2, 1).contiguous()                              # SoA
+    b = xn.permute(0, 2, 1)                                           # AoS view
+    pad = torch.full((B, N + 87, 3), float("nan"), device=dev)
+    pad[:, :N] = xn
+    c = pad[:, :N, :].permute(0, 2, 1)                                # sliced decoder output
+    outs, grads = [], []
+    for xx in (a, b, c):
+        xx = xx.detach().requires_grad_(True)
+        e = tpe.energy_per_conformation(xx)
+        e.sum().backward()
+        outs.append(e.detach().cpu().numpy())
+        grads.append(xx.grad.permute(0, 2, 1).cpu().numpy())
+    for o, g in zip(outs[1:], grads[1:]):
+        assert np.allclose(o, outs[0], rtol=2e-6)
+        assert rel(g, grads[0]) < 2e-6
+
+
+def test_clashing_structures_vs_oracle(dev, energy_objs, golden_topo, golden_energy):
+    """Garbage-decode regime: heavy noise puts many pairs below 1.9 A and 0.4 A (warp branch)."""
+    topo = golden_topo("bbcb")
+    tpe = energy_objs("bbcb")
+    rng = np.random.default_rng(11)
+    base = golden_energy("bbcb")["x"][0]
+    xs = np.stack([base + rng.normal(scale=s, size=base.shape).astype(np.float32) for s in (0.3, 2.0, 5.0)])
+    xs[2] *= 0.2                                                      # collapsed blob: massive clashes
+    x = torch.from_numpy(xs).to(dev).permute(0, 2, 1)
+    e = tpe.energy_per_conformation(x).double().cpu().numpy()
+    g = per_term_grads(tpe, x)
+    for q in range(len(xs)):
+        eo_e, eo_g = eo.energy_all(xs[q], topo)
+        for k, name in enumerate(TERMS):
+            assert abs(e[q, k] - eo_e[k]) < TOL * abs(eo_e[k]), (name, q, e[q, k], eo_e[k])
+            assert rel(g[k, q], eo_g[k]) < TOL, (name, q, rel(g[k, q], eo_g[k]))
+
+
+def test_full_lj_mode_vs_oracle(dev, energy_objs, golden_topo, golden_energy):
+    topo = golden_topo("bbcb")
+    tpe = energy_objs("bbcb", "full")
+    xs = golden_energy("bbcb")["x"][[1, 10]]
+    x = torch.from_numpy(xs).to(dev).permute(0, 2, 1).requires_grad_(True)
+    e = tpe.energy_per_conformation(x)
+    e[:, 3].sum().backward()
+    got_g = x.grad.permute(0, 2, 1).double().cpu().numpy()
+    ex = eo.exclusions(topo)
+    for q in range(2):
+        want_e, want_g = eo.nonbonded(xs[q], topo["atom_R"], topo["atom_e"], topo["atom_charges"], ex, full=True)
+        assert abs(float(e[q, 3]) - want_e) < TOL * abs(want_e)
+        assert rel(got_g[q], want_g) < TOL
+    # _cdist_nb_full on a 'repulsive' object and vice versa
+    rep = energy_objs("bbcb")
+    assert abs(float(rep._cdist_nb_full(x.detach())) - float(e[:, 3].sum())) < 1e-5 * abs(float(e[:, 3].sum()))
+
+
+def test_edge_batches(dev, energy_objs, golden_energy):
+    tpe = energy_objs("bbcb")
+    N = tpe.n_atoms
+    e = tpe.energy_per_conformation(torch.empty(0, 3, N, device=dev))
+    assert e.shape == (0, 4)
+    x1 = torch.from_numpy(golden_energy("bbcb")["x"][:1]).to(dev).permute(0, 2, 1)
+    e1 = tpe.energy_per_conformation(x1)
+    big = x1.expand(37, 3, N)                                         # stride_b = 0 broadcast batch
+    eb = tpe.energy_per_conformation(big)
+    assert torch.allclose(eb, e1.expand(37, 4), rtol=1e-6)
+    with pytest.raises(AssertionError):
+        tpe.energy_per_conformation(torch.zeros(1, 3, N + 1, device=dev))
+    with pytest.raises(RuntimeError):
+        tpe.energy_per_conformation(torch.zeros(1, 3, N))
+
+
+def test_nonfinite_inputs_stay_in_their_conformation(dev, energy_objs, golden_energy):
+    """NaN / inf propagate to that conformation only (the trainer's inf->1e35 / nansum guards rely on it)."""
+    tpe = energy_objs("bbcb")
+    xs = golden_energy("bbcb")["x"][:3].copy()
+    xs[1, 100, 0] = np.nan
+    x = torch.from_numpy(xs).to(dev).permute(0, 2, 1).requires_grad_(True)
+    e = tpe.energy_per_conformation(x)
+    e.nansum().backward()
+    e = e.detach().cpu().numpy()
+    assert np.isfinite(e[0]).all() and np.isfinite(e[2]).all()
+    assert np.isnan(e[1]).all()
+    g = x.grad.cpu().numpy()
+    assert np.isfinite(g[0]).all() and np.isfinite(g[2]).all()
+
+
+def test_large_batch_properties(dev, energy_objs, golden_energy):
+    """BASELINE batch sizes: translation / rotation invariance and sum of forces = 0 at B=64,
+    and a B=4096 batch equals 4096 copies of the small one (checksum of checksums)."""
+    en = golden_energy("bbcb")
+    tpe = energy_objs("bbcb")
+    base = torch.from_numpy(en["x"]).to(dev)                         # [14,N,3]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    idx = torch.arange(64) % base.shape[0]
+    xb = (base[idx] + 0.1 * torch.randn(64, base.shape[1], 3, generator=g).to(dev)).contiguous()
+    x = xb.permute(0, 2, 1).requires_grad_(True)
+    e = tpe.energy_per_conformation(x)
+    e.sum().backward()
+    net = x.grad.sum(dim=2)                                           # [B,3] net force
+    assert float(net.abs().max()) < 2e-2
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g).double())
+    moved = ((xb.double() - xb.double().mean(1, keepdim=True)) @ q.to(dev)).float().contiguous()
+    e2 = tpe.energy_per_conformation(moved.permute(0, 2, 1))
+    assert torch.allclose(e, e2, rtol=2e-5)
+    big = xb.repeat(64, 1, 1).permute(0, 2, 1)                        # B = 4096
+    eb = tpe.energy_per_conformation(big)
+    assert torch.equal(eb.view(64, 64, 4)[0], eb.view(64, 64, 4)[63])
+    assert torch.allclose(eb.view(64, 64, 4).double().sum(0), 64 * e.double(), rtol=1e-6)

@@ -1,0 +1,96 @@
+"""CPU: the product's C++ topology builder (C ABI mlp_topology_*) - bit-exact against the
+reference's vectors, error behaviour, and the exported symbol table."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, atominfo_from
+
+
+def test_library_exports_every_declared_symbol():
+    from molearn_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "molearn_b200.h")).read()
+    declared = set(re.findall(r"\b(mlp_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = ctypes.CDLL(_lib.library_path())
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().mlp_abi_version() == 1
+
+
+def test_builder_bit_exact(case, golden_topo, param_dir):
+    from molearn_b200 import Topology
+    g = golden_topo(case)
+    info = atominfo_from(g)
+    before = info.copy()
+    t = Topology(info, param_dir=param_dir)
+    assert np.array_equal(info, before)                             # caller's array untouched
+    assert np.array_equal(t.bond_idxs, g["bond_idxs"])
+    assert np.array_equal(t.angle_idxs, g["angle_idxs"])
+    assert np.array_equal(t.torsion_idxs, g["torsion_idxs"])
+    assert np.array_equal(t.bond_14_idxs, g["bond_14_idxs"])
+    assert np.array_equal(t.bond_para, g["bond_para"])
+    assert np.array_equal(t.angle_para, g["angle_para"])
+    assert np.array_equal(t.torsion_para, g["torsion_para"])
+    assert np.array_equal(t.amber_types, g["amber_types"])
+    assert np.array_equal(t.names, g["out_names"]) and np.array_equal(t.resnames, g["out_resnames"])
+    assert np.array_equal(t.atom_R, g["atom_R"]) and np.array_equal(t.atom_e, g["atom_e"])
+    assert np.array_equal(t.atom_charges.astype(np.float32), g["atom_charges"].astype(np.float32))
+    n = t.n_atoms
+    assert t.n_nb_pairs == int(g["nb_nnz_A"]) == n * (n - 1) // 2 - len(t.exclusions)
+    ex = t.exclusions
+    assert np.all(ex[:, 0] < ex[:, 1]) and len(np.unique(ex, axis=0)) == len(ex)
+
+
+def test_builder_matches_python_oracle_on_edge_inputs(param_dir):
+    """Ragged / unusual inputs the golden files do not hold: OXT, HIS variants, CHARMM names,
+    hydrogens with fix_h, a single residue, an empty list."""
+    from molearn_b200 import Topology
+    from oracle import topology_oracle as to
+    cases = {
+        "single_gly": [("N", "GLY", 1), ("CA", "GLY", 1), ("C", "GLY", 1), ("O", "GLY", 1)],
+        "oxt_his": [("N", "HIS", 5), ("CA", "HIS", 5), ("CB", "HIS", 5), ("CG", "HIS", 5), ("ND1", "HIS", 5),
+                    ("HD1", "HIS", 5), ("CD2", "HIS", 5), ("CE1", "HIS", 5), ("NE2", "HIS", 5), ("C", "HIS", 5),
+                    ("O", "HIS", 5), ("N", "HSD", 6), ("CA", "HSD", 6), ("C", "HSD", 6), ("O", "HSD", 6), ("OXT", "HSD", 6)],
+        "hydrogens": [("N", "ALA", 1), ("HN", "ALA", 1), ("CA", "ALA", 1), ("HA", "ALA", 1), ("CB", "ALA", 1),
+                      ("HB1", "ALA", 1), ("HB2", "ALA", 1), ("HB3", "ALA", 1), ("C", "ALA", 1), ("O", "ALA", 1),
+                      ("N", "SER", 2), ("H", "SER", 2), ("CA", "SER", 2), ("CB", "SER", 2), ("OG", "SER", 2),
+                      ("HG1", "SER", 2), ("C", "SER", 2), ("O", "SER", 2)],
+        "pro_ring": [("N", "PRO", 3), ("CD", "PRO", 3), ("CG", "PRO", 3), ("CB", "PRO", 3), ("CA", "PRO", 3),
+                     ("C", "PRO", 3), ("O", "PRO", 3), ("N", "TRP", 4), ("CA", "TRP", 4), ("C", "TRP", 4)],
+    }
+    for name, atoms in cases.items():
+        info = np.array(atoms, dtype=object)
+        fix_h = name == "hydrogens"
+        t = Topology(info, fix_h=fix_h, param_dir=param_dir)
+        o = to.build_topology(param_dir, list(info[:, 0]), list(info[:, 1]), [int(r) for r in info[:, 2]], fix_h=fix_h)
+        for k in ("bond_idxs", "angle_idxs", "torsion_idxs", "bond_para", "angle_para", "torsion_para"):
+            assert np.array_equal(getattr(t, k), o[k]), (name, k)
+        assert np.array_equal(t.amber_types, o["amber_types"]), name
+        assert np.array_equal(t.exclusions, to.exclusion_pairs(o).reshape(-1, 2)), name
+    empty = Topology(np.empty((0, 3), dtype=object), param_dir=param_dir)
+    assert empty.n_atoms == 0 and len(empty.bond_idxs) == 0
+
+
+def test_builder_errors(param_dir):
+    from molearn_b200 import Topology
+    with pytest.raises(KeyError):                                   # unknown residue (reference: KeyError, utils.py:489)
+        Topology(np.array([("N", "XYZ", 1)], dtype=object), param_dir=param_dir)
+    with pytest.raises(KeyError):                                   # unknown atom name
+        Topology(np.array([("QQ", "ALA", 1)], dtype=object), param_dir=param_dir)
+    with pytest.raises(FileNotFoundError):
+        Topology(np.array([("N", "ALA", 1)], dtype=object), param_dir="/nonexistent")
+
+
+def test_no_cpu_fallback(golden_topo):
+    import torch
+    from molearn_b200 import TorchProteinEnergy
+    info = atominfo_from(golden_topo("bbcb"))
+    with pytest.raises(RuntimeError):
+        TorchProteinEnergy(None, info, device=torch.device("cpu"))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):                           # no GPU: create fails loudly
+            TorchProteinEnergy(None, info, device=torch.device("cuda:0"))
