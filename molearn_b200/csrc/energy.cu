@@ -46,6 +46,9 @@ constexpr int NF = 4;            // torsion Fourier orders kept (ff14SB periods 
 constexpr int NB_T = 128;        // non-bonded tile edge (atoms)
 constexpr int NB_NI = 4;         // i-atoms per lane
 constexpr int NB_WARPS = 4;      // warps per CTA, one work item each
+#ifndef NB_MINB
+#define NB_MINB 3
+#endif
 constexpr float LJ_K = 1.9f, C_K = 0.4f;  // warp thresholds, torch_protein_energy.py:233-234
 constexpr float CLAMP = 0.999999f;        // acos clamp, :289
 
@@ -160,11 +163,15 @@ __device__ __forceinline__ void angle_term(const float4* sc, float4* slots, cons
     float dt = th - r.th0;
     if (r.ij & OWNER) e += r.kf * dt * dt;
     if (grad) {
-        // dE/dc = 2K(theta-theta0) * (-1/sqrt(1-c^2)); torch.clamp passes no gradient outside
-        float dEdc = (c > -CLAMP && c < CLAMP) ? -w * 2.f * r.kf * dt * rsqrtf(1.f - c * c) : 0.f;
-        if (c != c) dEdc = c;
-        float3 gi = (dEdc * inv12) * v2 - (dEdc * c / n1) * v1;
-        float3 gk = (dEdc * inv12) * v1 - (dEdc * c / n2) * v2;
+        // dtheta/dv1 = v1 x (v1 x v2) / (|v1|^2 |v1 x v2|), dtheta/dv2 = -v2 x (v1 x v2) / (|v2|^2 |v1 x v2|):
+        // the cross-product form of -1/sqrt(1-c^2) * dc/dv, which does not cancel near c = +-1.
+        // torch.clamp passes no gradient outside the clamp, so the term is dropped there.
+        float3 n = cross(v1, v2);
+        float nn = dot(n, n);
+        float coef = (c > -CLAMP && c < CLAMP) ? w * 2.f * r.kf * dt * rsqrtf(nn) : 0.f;
+        if (c != c) coef = c;
+        float3 gi = (coef / n1) * cross(v1, n);
+        float3 gk = (-coef / n2) * cross(v2, n);
         slots[r.s_ij & 0xffffu] = f4(gi);
         slots[r.s_k] = f4(gk);
         slots[r.s_ij >> 16] = f4(-1.f * (gi + gk));
@@ -373,60 +380,79 @@ __device__ __forceinline__ void warp_fn(float d, float k, float& w, float& dw) {
     else { float ex = expf(d - k); w = ex - 1.f + k; dw = ex; }
 }
 
-// One micro-tile: NB_NI i-atoms (registers) x 4 j-atoms.  FAST: every pair has d > 1.9 A.
-template <bool FAST, bool MASKED, bool FULL>
+// Squared distance below which a pair leaves the fast path (w(d,1.9) = d needs d > 1.9 A; the
+// margin covers the 2-ulp rsqrt).  Pairs closer than this are evaluated by the fast path at the
+// clamped distance sqrt(NB_THR2) - a small, finite value - and then corrected by nb_pair_fix().
+constexpr float NB_THR2 = LJ_K * LJ_K * 1.0001f;
+constexpr float NB_MASKED_R2 = 1.0e4f;  // stand-in r^2 of statically excluded pairs (their parameters are zeroed)
+
+// Fast-path pair term at squared distance r2c >= NB_THR2.  Returns s = -(dE/dd)/d; adds 12*E_lj to
+// Sl and E_coulomb to Sc.
+template <bool FULL>
+__device__ __forceinline__ float nb_pair_fast(float r2c, float Rij, float e12, float qq, float& Sl, float& Sc) {
+    float inv = rsqrt_fast(r2c);
+    float t = Rij * inv;
+    float t2 = t * t;
+    float t6 = t2 * t2 * t2;
+    float u6 = e12 * t6;
+    float ec = qq * inv;
+    float u;
+    if (FULL) { u = fmaf(u6, t6 - 1.f, ec); Sl = fmaf(u6, t6 - 2.f, Sl); }
+    else { u = fmaf(u6, t6, ec); Sl = fmaf(u6, t6, Sl); }
+    Sc = fmaf(qq, inv, Sc);
+    return u * (inv * inv);
+}
+
+// Exact pair term (any distance), minus what the fast path added for this pair at the clamped
+// distance.  Rare path (clashing structures): kept out of line to protect the hot loop's registers
+// and instruction cache.  Returns (ds, dSl, dSc).
+template <bool FULL>
+__device__ __noinline__ float3 nb_pair_fix(float r2, float Rij, float e12, float qq) {
+    float Sl_f = 0.f, Sc_f = 0.f;
+    float s_f = nb_pair_fast<FULL>(NB_THR2, Rij, e12, qq, Sl_f, Sc_f);
+    // the fast path multiplied s by the true (dx,dy,dz); so must the correction
+    float d = sqrtf(r2);
+    float dinv = r2 > 0.f ? 1.f / d : 0.f;  // coincident atoms: zero force (cdist's backward does the same)
+    float w1, dw1, w2, dw2;
+    warp_fn(d, LJ_K, w1, dw1);
+    warp_fn(d, C_K, w2, dw2);
+    float iw1 = 1.f / w1, iw2 = 1.f / w2;
+    float t = Rij * iw1;
+    float t2 = t * t;
+    float t6 = t2 * t2 * t2;
+    float u6 = e12 * t6;
+    float ec = qq * iw2;
+    float ulj, sl;
+    if (FULL) { ulj = u6 * (t6 - 1.f); sl = u6 * (t6 - 2.f); }
+    else { ulj = u6 * t6; sl = ulj; }
+    float s = (ulj * iw1 * dw1 + ec * iw2 * dw2) * dinv;
+    return make_float3(s - s_f, sl - Sl_f, ec - Sc_f);
+}
+
+// One micro-tile: NB_NI i-atoms (registers) x 4 j-atoms, fast path with clamped distance.
+// m16: bit (4a+b) = pair allowed (MASKED tiles).  Returns the smallest true r^2 of the allowed pairs.
+template <bool MASKED, bool FULL>
 __device__ __forceinline__ float nb_micro(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
-                                         const float (&hRj)[4], const float (&sej)[4], const uint32_t (&mw)[NB_NI],
-                                         float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
-    float rmin = 1e30f;  // FAST: smallest squared distance seen (the caller validates the fast path with it)
+                                          const float2 (&pj)[4], uint32_t m16,
+                                          float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
+    float rmin = 1e30f;
 #pragma unroll
     for (int a = 0; a < NB_NI; ++a) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             float dx = xi[a].x - xj[b].x, dy = xi[a].y - xj[b].y, dz = xi[a].z - xj[b].z;
             float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            float e12 = pi[a].y * sej[b];
+            float e12 = pi[a].y * pj[b].y;
             float qq = xi[a].w * xj[b].w;
-            float Rij = pi[a].x + hRj[b];
+            float Rij = pi[a].x + pj[b].x;
             if (MASKED) {
-                bool on = (mw[a] >> b) & 1u;
-                r2 = on ? r2 : 1.0f;
+                bool on = (m16 >> (4 * a + b)) & 1u;
+                r2 = on ? r2 : NB_MASKED_R2;
                 e12 = on ? e12 : 0.f;
                 qq = on ? qq : 0.f;
             }
-            float inv = rsqrt_fast(r2);
-            float s;
-            if (FAST) {
-                rmin = fminf(rmin, r2);
-                float t = Rij * inv;
-                float t2 = t * t;
-                float t6 = t2 * t2 * t2;
-                float u6 = e12 * t6;
-                float ec = qq * inv;
-                float u;
-                if (FULL) { u = fmaf(u6, t6 - 1.f, ec); Sl = fmaf(u6, t6 - 2.f, Sl); }
-                else { u = fmaf(u6, t6, ec); Sl = fmaf(u6, t6, Sl); }
-                Sc = fmaf(qq, inv, Sc);
-                s = u * (inv * inv);
-            } else {
-                float d = r2 * inv;
-                d = r2 > 0.f ? d : 0.f;
-                float dinv = r2 > 0.f ? inv : 0.f;  // coincident atoms: zero force like autograd's sqrt'(0) guard in cdist
-                float w1, dw1, w2, dw2;
-                warp_fn(d, LJ_K, w1, dw1);
-                warp_fn(d, C_K, w2, dw2);
-                float iw1 = 1.f / w1, iw2 = 1.f / w2;
-                float t = Rij * iw1;
-                float t2 = t * t;
-                float t6 = t2 * t2 * t2;
-                float u6 = e12 * t6;
-                float ec = qq * iw2;
-                float ulj;
-                if (FULL) { ulj = u6 * (t6 - 1.f); Sl = fmaf(u6, t6 - 2.f, Sl); }
-                else { ulj = u6 * t6; Sl += ulj; }
-                Sc += ec;
-                s = (ulj * iw1 * dw1 + ec * iw2 * dw2) * dinv;
-            }
+            rmin = fminf(rmin, r2);
+            float s = nb_pair_fast<FULL>(fmaxf(r2, NB_THR2), Rij, e12, qq, Sl, Sc);
             Fi[a].x = fmaf(s, dx, Fi[a].x); Fi[a].y = fmaf(s, dy, Fi[a].y); Fi[a].z = fmaf(s, dz, Fi[a].z);
             Fj[b].x = fmaf(s, dx, Fj[b].x); Fj[b].y = fmaf(s, dy, Fj[b].y); Fj[b].z = fmaf(s, dz, Fj[b].z);
         }
@@ -434,57 +460,56 @@ __device__ __forceinline__ float nb_micro(const float4 (&xi)[NB_NI], const float
     return rmin;
 }
 
-// Sum 12 per-lane values across the warp by halving exchange (13 shuffles instead of 60).
-// On return lane L holds, in `out`, the total of value index vidx(L); lanes with valid==false hold padding.
-__device__ __forceinline__ float reduce12(const float3 (&Fj)[4], int lane, int& vidx, bool& valid) {
-    float v[16];
+// Correction pass over a micro-tile that holds at least one pair closer than sqrt(NB_THR2).
+template <bool MASKED, bool FULL>
+__device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
+                                             const float2 (&pj)[4], uint32_t m16,
+                                             float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
+    // Launder the operands: without this the compiler shares dx/r2/... with the hot micro-tile
+    // and keeps 60+ values alive (spilled to local memory) just in case this path runs.
+    float4 yi[NB_NI], yj[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) { v[3 * b] = Fj[b].x; v[3 * b + 1] = Fj[b].y; v[3 * b + 2] = Fj[b].z; }
-    v[12] = v[13] = v[14] = v[15] = 0.f;
-    // step 1: 16 -> 8 (xor 16).  Only 12 are real: upper half indices 8..15 hold 8..11 real.
-    float a8[8];
-    bool hi = lane & 16;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        float send = hi ? v[k] : v[k + 8];
-        float keep = hi ? v[k + 8] : v[k];
-        a8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    for (int a = 0; a < NB_NI; ++a) {
+        yi[a] = xi[a];
+        asm volatile("" : "+f"(yi[a].x), "+f"(yi[a].y), "+f"(yi[a].z), "+f"(yi[a].w));
     }
-    float a4[4];
-    bool h8 = lane & 8;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float send = h8 ? a8[k] : a8[k + 4];
-        float keep = h8 ? a8[k + 4] : a8[k];
-        a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    for (int b = 0; b < 4; ++b) {
+        yj[b] = xj[b];
+        asm volatile("" : "+f"(yj[b].x), "+f"(yj[b].y), "+f"(yj[b].z), "+f"(yj[b].w));
     }
-    float a2[2];
-    bool h4 = lane & 4;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        float send = h4 ? a4[k] : a4[k + 2];
-        float keep = h4 ? a4[k + 2] : a4[k];
-        a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    for (int a = 0; a < NB_NI; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float dx = yi[a].x - yj[b].x, dy = yi[a].y - yj[b].y, dz = yi[a].z - yj[b].z;
+            float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            bool on = !MASKED || ((m16 >> (4 * a + b)) & 1u);
+            // NaN coordinates: !(r2 >= thr) is true -> exact path -> NaN propagates
+            if (on && !(r2 >= NB_THR2)) {
+                float3 c = nb_pair_fix<FULL>(r2, pi[a].x + pj[b].x, pi[a].y * pj[b].y, yi[a].w * yj[b].w);
+                Fi[a].x = fmaf(c.x, dx, Fi[a].x); Fi[a].y = fmaf(c.x, dy, Fi[a].y); Fi[a].z = fmaf(c.x, dz, Fi[a].z);
+                Fj[b].x = fmaf(c.x, dx, Fj[b].x); Fj[b].y = fmaf(c.x, dy, Fj[b].y); Fj[b].z = fmaf(c.x, dz, Fj[b].z);
+                Sl += c.y; Sc += c.z;
+            }
+        }
     }
-    bool h2 = lane & 2;
-    float send = h2 ? a2[0] : a2[1];
-    float keep = h2 ? a2[1] : a2[0];
-    float a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-    vidx = (hi ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
-    valid = vidx < 12 && !(lane & 1);
-    return a1;
 }
 
+// One warp = one (conformation, tile pair).  Lane L owns i-atoms i0+L+32a (a<4) for the whole
+// tile; the 32 groups of 4 j-atoms rotate through the lanes (lane L works on group (L+r)%32 at
+// step r) together with their force accumulators, so Newton's third law costs 12 shuffles per
+// 16 pairs and no reduction.
 template <bool GRAD, bool FULL>
-__global__ void __launch_bounds__(NB_WARPS * 32)
+__global__ void __launch_bounds__(NB_WARPS * 32, NB_MINB)
 nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const int2* __restrict__ pairs,
           const uint32_t* __restrict__ masks, int n_pairs, int n_masked, int Npad, int N, int B,
           float* __restrict__ grad, long sgb, long sgc, long sgn, const float* __restrict__ weights,
           double* __restrict__ acc) {
+    // j tile, group-minor: atom 4g+b lives at [b*32+g] so that lanes (different g) never conflict
     __shared__ float4 s_xj[NB_WARPS][NB_T];
-    __shared__ float s_hR[NB_WARPS][NB_T];
-    __shared__ float s_se[NB_WARPS][NB_T];
+    __shared__ float2 s_pj[NB_WARPS][NB_T];
+    __shared__ uint32_t s_m[NB_WARPS][NB_T * 4];   // uint16 [g][lane] pair masks, as words
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long item = (long)blockIdx.x * NB_WARPS + warp;
     if (item >= (long)B * n_pairs) return;
@@ -494,6 +519,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     const int2 IJ = pairs[p];
     const int i0 = IJ.x * NB_T, j0 = IJ.y * NB_T;
     const float4* xb = xq + (long)b * Npad;
+    const bool masked = p < n_masked;
 
     float4 xi[NB_NI];
     float2 pi[NB_NI];
@@ -505,79 +531,63 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
         Fi[a] = make_float3(0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int a = 0; a < NB_T / 32; ++a) {
-        int jj = lane + 32 * a;
-        s_xj[warp][jj] = xb[j0 + jj];
-        float2 pj = par[j0 + jj];
-        s_hR[warp][jj] = pj.x;
-        s_se[warp][jj] = pj.y;
+    for (int k = 0; k < NB_T / 32; ++k) {
+        int jj = lane + 32 * k;
+        int slot = (jj & 3) * 32 + (jj >> 2);
+        s_xj[warp][slot] = xb[j0 + jj];
+        s_pj[warp][slot] = par[j0 + jj];
+    }
+    if (masked) {
+        const uint4* src = reinterpret_cast<const uint4*>(masks + (long)p * (NB_T * 4));
+        uint4* dst = reinterpret_cast<uint4*>(s_m[warp]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = src[lane + 32 * k];
     }
     __syncwarp();
 
     float Sl = 0.f, Sc = 0.f;
-    const bool masked = p < n_masked;
-    uint4 mrow[NB_NI];
-    if (masked) {
+    float3 Fj[4];
 #pragma unroll
-        for (int a = 0; a < NB_NI; ++a)
-            mrow[a] = reinterpret_cast<const uint4*>(masks)[((long)p * NB_T + lane + 32 * a)];
-    }
-    float* gb = GRAD ? grad + (long)b * sgb : nullptr;
+    for (int q = 0; q < 4; ++q) Fj[q] = make_float3(0.f, 0.f, 0.f);
+    const int src_lane = (lane + 1) & 31;
+    const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m[warp]);
 
 #pragma unroll 1
-    for (int wd = 0; wd < 4; ++wd) {
-        uint32_t cw[NB_NI];
+    for (int r = 0; r < 32; ++r) {
+        const int g = (lane + r) & 31;
+        float4 xj[4];
+        float2 pj[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { xj[q] = s_xj[warp][q * 32 + g]; pj[q] = s_pj[warp][q * 32 + g]; }
         if (masked) {
-#pragma unroll
-            for (int a = 0; a < NB_NI; ++a) cw[a] = wd == 0 ? mrow[a].x : wd == 1 ? mrow[a].y : wd == 2 ? mrow[a].z : mrow[a].w;
+            const uint32_t m16 = sm16[g * 32 + lane];
+            float rmin = nb_micro<true, FULL>(xi, pi, xj, pj, m16, Fi, Fj, Sl, Sc);
+            if (!(rmin >= NB_THR2)) nb_micro_fix<true, FULL>(xi, pi, xj, pj, m16, Fi, Fj, Sl, Sc);
+        } else {
+            float rmin = nb_micro<false, FULL>(xi, pi, xj, pj, 0xffffu, Fi, Fj, Sl, Sc);
+            if (!(rmin >= NB_THR2)) nb_micro_fix<false, FULL>(xi, pi, xj, pj, 0xffffu, Fi, Fj, Sl, Sc);
         }
-#pragma unroll 1
-        for (int it = 0; it < 8; ++it) {
-            const int jb = wd * 32 + it * 4;
-            float4 xj[4];
-            float hRj[4], sej[4];
-            float4 h4 = *reinterpret_cast<const float4*>(&s_hR[warp][jb]);
-            float4 e4 = *reinterpret_cast<const float4*>(&s_se[warp][jb]);
-            hRj[0] = h4.x; hRj[1] = h4.y; hRj[2] = h4.z; hRj[3] = h4.w;
-            sej[0] = e4.x; sej[1] = e4.y; sej[2] = e4.z; sej[3] = e4.w;
+        if (GRAD) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) xj[q] = s_xj[warp][jb + q];
-            float3 Fj[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) Fj[q] = make_float3(0.f, 0.f, 0.f);
-            uint32_t mw[NB_NI];
-            if (masked) {
-#pragma unroll
-                for (int a = 0; a < NB_NI; ++a) { mw[a] = cw[a] & 15u; cw[a] >>= 4; }
-                nb_micro<false, true, FULL>(xi, pi, xj, hRj, sej, mw, Fi, Fj, Sl, Sc);
-            } else {
-                // optimistic fast path (w(d,k) = d); valid only if d > 1.9 A for all 16 pairs of
-                // this lane, otherwise roll the accumulators back and redo the micro-tile exactly.
-                // NaN coordinates: the comparison is false -> slow path, which propagates NaN.
-                float3 Fi0[NB_NI];
-#pragma unroll
-                for (int a = 0; a < NB_NI; ++a) Fi0[a] = Fi[a];
-                const float Sl0 = Sl, Sc0 = Sc;
-                float rmin = nb_micro<true, false, FULL>(xi, pi, xj, hRj, sej, mw, Fi, Fj, Sl, Sc);
-                if (!(rmin > LJ_K * LJ_K * 1.0001f)) {
-#pragma unroll
-                    for (int a = 0; a < NB_NI; ++a) Fi[a] = Fi0[a];
-                    Sl = Sl0; Sc = Sc0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) Fj[q] = make_float3(0.f, 0.f, 0.f);
-                    nb_micro<false, false, FULL>(xi, pi, xj, hRj, sej, mw, Fi, Fj, Sl, Sc);
-                }
-            }
-            if (GRAD) {
-                int vidx; bool valid;
-                float tot = reduce12(Fj, lane, vidx, valid);
-                int ja = j0 + jb + vidx / 3, c = vidx - 3 * (vidx / 3);
-                // grad_j = +s*(ri-rj) summed (dE/drj = -dE/dd * (ri-rj)/d, s = -dE/dd / d)
-                if (valid && ja < N) atomicAdd(gb + (long)ja * sgn + c * sgc, wnb * tot);
+            for (int q = 0; q < 4; ++q) {
+                Fj[q].x = __shfl_sync(0xffffffffu, Fj[q].x, src_lane);
+                Fj[q].y = __shfl_sync(0xffffffffu, Fj[q].y, src_lane);
+                Fj[q].z = __shfl_sync(0xffffffffu, Fj[q].z, src_lane);
             }
         }
     }
     if (GRAD) {
+        // after 32 rotations lane L holds the finished forces of group L (atoms j0+4L+q);
+        // grad_i = -sum s*(ri-rj), grad_j = +sum s*(ri-rj)   (s = -(dE/dd)/d)
+        float* gb = grad + (long)b * sgb;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int ja = j0 + 4 * lane + q;
+            if (ja < N) {
+                float* g = gb + (long)ja * sgn;
+                atomicAdd(g, wnb * Fj[q].x); atomicAdd(g + sgc, wnb * Fj[q].y); atomicAdd(g + 2 * sgc, wnb * Fj[q].z);
+            }
+        }
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) {
             int ia = i0 + lane + 32 * a;
@@ -817,12 +827,14 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     for (auto& kv : ex) {
         const int I = kv.first.first, J = kv.first.second;
         pairs.push_back(make_int2(I, J));
-        std::vector<uint32_t> m((size_t)NB_T * 4, 0xffffffffu);
-        auto clear = [&](int li, int lj) { m[(size_t)li * 4 + lj / 32] &= ~(1u << (lj % 32)); };
+        std::vector<uint16_t> m16((size_t)32 * 32, 0xffffu);
+        auto clear = [&](int li, int lj) { m16[(size_t)(lj >> 2) * 32 + (li & 31)] &= (uint16_t)~(1u << (4 * (li >> 5) + (lj & 3))); };
         if (I == J)
             for (int li = 0; li < NB_T; ++li)
                 for (int lj = 0; lj <= li; ++lj) clear(li, lj);
         for (auto& pr : kv.second) clear(pr.first - I * NB_T, pr.second - J * NB_T);
+        std::vector<uint32_t> m((size_t)NB_T * 4);
+        std::memcpy(m.data(), m16.data(), m.size() * sizeof(uint32_t));
         masks.insert(masks.end(), m.begin(), m.end());
     }
     E->n_masked = (int)pairs.size();
@@ -931,7 +943,9 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
                     float* energies, float* grad, int64_t sgb, int64_t sgc, int64_t sgn,
                     const float* weights, uint32_t term_mask, uint32_t flags,
                     void* workspace, int64_t workspace_bytes, void* stream_) {
-    if (!e || !x || B < 0 || !workspace || (term_mask & ~MLP_TERM_ALL)) { mlp_set_error("mlp_energy_eval: bad argument"); return MLP_E_ARG; }
+    if (!e || B < 0 || (term_mask & ~MLP_TERM_ALL)) { mlp_set_error("mlp_energy_eval: bad argument"); return MLP_E_ARG; }
+    if (B == 0 || e->N == 0) { e->last_launches = 0; return MLP_OK; }  // empty batch: nothing to do (pointers may be null)
+    if (!x || !workspace) { mlp_set_error("mlp_energy_eval: null x / workspace"); return MLP_E_ARG; }
     if (workspace_bytes < mlp_energy_workspace_bytes(e, B)) { mlp_set_error("mlp_energy_eval: workspace too small"); return MLP_E_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(workspace) & 15) { mlp_set_error("mlp_energy_eval: workspace must be 16-byte aligned"); return MLP_E_ARG; }
     e->last_launches = 0;
