@@ -1,3 +1,4 @@
 from .reducers import rmsd_to_targets
+from .analyser import MolearnAnalysis, shard_range
 
-__all__ = ["rmsd_to_targets"]
+__all__ = ["MolearnAnalysis", "rmsd_to_targets", "shard_range"]

@@ -1,0 +1,109 @@
+"""GPU: latent-grid scan and physics trainer through the public classes, checked against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import energy_oracle as eo
+
+pytestmark = pytest.mark.gpu
+ATOMS = ("N", "CA", "CB", "C", "O")
+
+
+@pytest.fixture(scope="module")
+def murd_data():
+    from molearn_b200.data import CoordinateSet
+    d = load_golden("murd_input")
+    keep = np.isin(d["names"], ATOMS)
+    info = np.empty((int(keep.sum()), 3), dtype=object)
+    info[:, 0], info[:, 1], info[:, 2] = list(d["names"][keep]), list(d["resnames"][keep]), [int(r) for r in d["resids"][keep]]
+    return CoordinateSet(info, np.ascontiguousarray(d["coords"][:, keep])).prepare_dataset()
+
+
+@pytest.fixture(scope="module")
+def analysis(murd_data):
+    from molearn_b200.analysis import MolearnAnalysis
+    from molearn_b200.models import AutoEncoder
+    torch.manual_seed(0)
+    net = AutoEncoder(out_points=murd_data.dataset.shape[1]).to("cuda:0")
+    ma = MolearnAnalysis(batch_size=16)
+    ma.set_network(net)
+    ma.set_dataset("train", murd_data)
+    ma.setup_grid(samples=6, padding=0.1)
+    return ma
+
+
+def decoded_angstrom(ma):
+    with torch.no_grad():
+        z = ma._encoded["grid"].reshape(-1, 2).to(ma.device)
+        return (ma.network.decode(z)[:, :ma.n_atoms, :] * ma.stdval + ma.meanval).double().cpu().numpy()
+
+
+def test_scan_physics_vs_oracle(analysis):
+    ma = analysis
+    total, xv, yv = ma.scan_physics()
+    assert total.shape == (6, 6) and len(xv) == 6 and len(yv) == 6
+    topo = load_golden("topo_bbcb")
+    dec = decoded_angstrom(ma)
+    for p in (0, 17, 35):
+        want, _ = eo.energy_all(dec[p], topo, want_grad=False)
+        got = [ma.surfaces[f"Physics_{n}"].reshape(-1)[p] for n in ("bond", "angle", "torsion", "nb")]
+        for k in range(4):
+            assert abs(got[k] - want[k]) < 2e-5 * abs(want[k]), (p, k, got[k], want[k])   # decode runs twice (TF32 noise aside: same kernels)
+        assert abs(total.reshape(-1)[p] - want.sum()) < 2e-5 * abs(want.sum())
+
+
+def test_scan_error_from_target(analysis, murd_data):
+    ma = analysis
+    surf, _, _ = ma.scan_error_from_target("train", index=3, align=False)
+    dec = decoded_angstrom(ma)
+    tgt = murd_data.coords[3].astype(np.float64)
+    want = np.sqrt(((dec - tgt) ** 2).sum(2).mean(1)).reshape(6, 6)
+    assert np.allclose(surf, want, rtol=2e-5)
+    assert "RMSD_from_train_index_3" in ma.surfaces
+    with pytest.raises(Exception):
+        ma.scan_error_from_target("train")                               # 16 frames, no index
+
+
+def test_scan_scores_and_error(analysis, murd_data):
+    ma = analysis
+    tg = torch.from_numpy(murd_data.coords[:4])
+    rows = ma.scan_scores(targets=tg)
+    assert rows.shape == (36, 8)
+    assert np.allclose(rows[:, 0].numpy().reshape(6, 6), ma.surfaces["Physics_bond"], rtol=1e-5)
+    assert np.allclose(rows[:, 7].numpy().reshape(6, 6), ma.scan_error_from_target("train", index=3, align=False)[0], rtol=1e-5)
+    rmsd, drift, _, _ = ma.scan_error()
+    assert rmsd.shape == (6, 6) and np.isfinite(rmsd).all() and np.isfinite(drift).all()
+
+
+def test_physics_trainer_step(murd_data):
+    from molearn_b200.models import AutoEncoder
+    from molearn_b200.trainers import Torch_Physics_Trainer
+    torch.manual_seed(0)
+    tr = Torch_Physics_Trainer(device="cuda:0")
+    tr.set_data(murd_data)
+    tr.set_autoencoder(AutoEncoder, out_points=murd_data.dataset.shape[1])
+    tr.prepare_optimiser()
+    tr.prepare_physics(physics_scaling_factor=0.1)
+    batch = murd_data.dataset[:8].to("cuda:0")
+    before = [p.detach().clone() for p in tr.autoencoder.decoder.parameters()]
+    res = tr.training_iteration(batch)
+    for k in ("physics_loss", "bond_energy", "angle_energy", "torsion_energy", "mse_loss", "loss"):
+        assert k in res and torch.isfinite(res[k]).all(), k
+    assert any(not torch.equal(a, b) for a, b in zip(before, tr.autoencoder.decoder.parameters()))
+    # the physics terms are the oracle's bonded energies of the generated structures
+    gen = (tr._internal["generated"].detach() * tr.std + tr.mean).double().cpu().numpy()
+    topo = load_golden("topo_bbcb")
+    want = np.mean([eo.bonded(g, topo, want_grad=False)[0] for g in gen], axis=0)
+    got = [float(res[k]) for k in ("bond_energy", "angle_energy", "torsion_energy")]
+    for k in range(3):
+        assert abs(got[k] - want[k]) < 1e-5 * want[k]
+    # and the physics gradient reaches the decoder: d(physics)/d(decoder params) != 0
+    tr.autoencoder.zero_grad()
+    out = tr.common_step(batch)
+    out.update(tr.common_physics_step(batch, tr._internal["encoded"]))
+    out["physics_loss"].backward()
+    gnorm = sum(float(p.grad.abs().sum()) for p in tr.autoencoder.decoder.parameters() if p.grad is not None)
+    assert gnorm > 0 and np.isfinite(gnorm)
+    v = tr.valid_step(batch)
+    assert torch.isfinite(v["loss"])
