@@ -17,6 +17,7 @@
  *     else is host memory.
  *   - no entry point allocates device memory, synchronises the device or copies to the host
  *     after mlp_energy_create(); all work is ordered on the cudaStream_t passed as `stream`.
+ *   - no kernel uses atomics: every output is a fixed-order sum, bit-reproducible run to run.
  */
 #ifndef MOLEARN_B200_H
 #define MOLEARN_B200_H
@@ -119,8 +120,14 @@ int mlp_device_count(void);
 int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_energy** out);
 void mlp_energy_destroy(mlp_energy* e);
 
-/* Bytes of scratch device memory mlp_energy_eval needs for a batch of B conformations. */
-int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B);
+/* Bytes of scratch device memory mlp_energy_eval needs for a batch of B conformations evaluated with
+ * this term_mask, with (want_grad != 0) or without a gradient output. */
+int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B, uint32_t term_mask, int want_grad);
+
+/* Packing facts, for benchmarks and tests: info[0..7] = bonded tiles, atoms per bonded tile, max
+ * gradient contributions per atom, bonded shared memory bytes per CTA, NB tiles per edge, NB tile
+ * pairs, masked NB tile pairs, padded atom count. */
+int mlp_energy_info(const mlp_energy* e, int64_t info[8]);
 
 /* Energies and (optionally) gradient of B conformations.
  *
@@ -133,7 +140,7 @@ int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B);
  *   grad       dev, same logical shape as x addressed with (sgb,sgc,sgn), or NULL for
  *              energy only.  grad = sum_t w[b,t] * dE_t/dx over the terms in term_mask.
  *   weights    dev [B,4] fp32 or NULL (= all ones).  The upstream gradient of a backward pass.
- *   workspace  dev, >= mlp_energy_workspace_bytes(e,B) bytes, 16-byte aligned
+ *   workspace  dev, >= mlp_energy_workspace_bytes(e,B,term_mask,grad!=NULL) bytes, 16-byte aligned
  *   stream     cudaStream_t
  * Non-finite coordinates are not an error: they propagate into that conformation's outputs.
  */
@@ -150,7 +157,7 @@ int mlp_energy_last_launches(const mlp_energy* e);
 /* Optional per-kernel timing for benchmarks.  While enabled, mlp_energy_eval brackets each of
  * its kernels with CUDA events on the launching stream.  mlp_energy_profile_read waits for the
  * recorded events, returns the summed milliseconds and launch counts per kernel
- * (0 = nb pack, 1 = bonded, 2 = non-bonded pair kernel, 3 = unused) and resets the totals. */
+ * (0 = nb pack, 1 = bonded, 2 = non-bonded pair kernel, 3 = non-bonded force reduction) and resets the totals. */
 int mlp_energy_profile(mlp_energy* e, int enable);
 int mlp_energy_profile_read(mlp_energy* e, double ms[4], int64_t counts[4]);
 

@@ -26,7 +26,8 @@ SYMBOLS = {
     "mlp_device_count": (c_int, []),
     "mlp_energy_create": (c_int, [c_void_p, c_int, c_uint32, POINTER(c_void_p)]),
     "mlp_energy_destroy": (None, [c_void_p]),
-    "mlp_energy_workspace_bytes": (c_int64, [c_void_p, c_int64]),
+    "mlp_energy_workspace_bytes": (c_int64, [c_void_p, c_int64, c_uint32, c_int]),
+    "mlp_energy_info": (c_int, [c_void_p, c_void_p]),
     "mlp_energy_eval": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                 c_void_p, c_int64, c_int64, c_int64, c_void_p, c_uint32, c_uint32,
                                 c_void_p, c_int64, c_void_p]),

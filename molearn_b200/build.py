@@ -45,7 +45,8 @@ def _stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     if force or _stale():
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+        extra = os.environ.get("MLP_NVCC_DEFS", "").split()          # e.g. "-DNB_MINB=4" when tuning
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

@@ -4,24 +4,28 @@
 // Replaces the ATen op chains of TorchProteinEnergy._roll_bond_angle_torsion_loss
 // (src/molearn/loss_functions/torch_protein_energy.py:276-305, ~500 launches) and _cdist_nb /
 // _cdist_nb_full (:224-239, ~15 dense [B,N,N] passes) by one launch each.  FP32 on the FMA
-// pipes; no tensor cores (not a dense contraction); O(N) memory.
+// pipes; no tensor cores (not a dense contraction); O(N) memory; NO ATOMICS anywhere - every
+// output is produced by a fixed-order sum, so results are bit-reproducible run to run.
 //
-// Bonded kernel (bandwidth / issue bound)
+// Bonded kernel
 //   CTA = (atom tile, chunk of conformations).  The tile's term records live in REGISTERS for
 //   the whole chunk, so topology is read once per CTA, not once per conformation.  Per
 //   conformation: coordinates of the tile (+halo) are staged in shared memory as float4, each
 //   thread evaluates its terms and writes every role's gradient to a private shared-memory slot;
-//   slots are laid out so that each atom's incoming contributions are contiguous, and one thread
-//   per atom sums its range and writes the gradient once - no atomics.  Terms that straddle a
-//   tile boundary are evaluated by both tiles (energy counted by the owner of role 0).
+//   slot (atom a, k-th contribution) lives at [k*stride + a], so the term phase writes and the
+//   per-atom gather reads are both bank-conflict-free for neighbouring atoms; one thread per atom
+//   sums its column and writes the gradient once.  Terms that straddle a tile boundary are
+//   evaluated by both tiles (energy counted by the owner of role 0).
 //
-// Non-bonded kernel (FP32 FMA bound)
+// Non-bonded kernel
 //   Work item = (conformation, 128x128 atom tile pair J>=I), one warp each.  A lane owns NI=4
-//   i-atoms in registers; j-atoms are broadcast from shared memory 4 at a time; Newton's third
-//   law is used, the j-forces being reduced across the warp by a halving exchange and added to
-//   the gradient with RED.  Tile pairs that contain excluded (1-2/1-3/1-4) pairs or the diagonal
-//   carry a 128x128 bit mask applied in registers; all other tiles run a fast path (d > 1.9 A
-//   everywhere: w(d,k) = d) guarded by a min-distance test per micro-tile.
+//   i-atoms in registers for the whole tile; the 32 groups of 4 j-atoms rotate through the lanes
+//   together with their force accumulators (Newton's third law for 12 shuffles per 16 pairs).
+//   Tile pairs that contain excluded (1-2/1-3/1-4) pairs or the diagonal carry a 128x128 bit mask
+//   applied in registers.  The hot loop is the fast path w(d,k) = d at a clamped distance; the rare
+//   pairs closer than 1.9 A are corrected exactly, out of line.  Each item writes its partial
+//   forces to a scratch buffer; a second kernel sums, per atom, the partials of the tile pairs in
+//   its row and column in a fixed order and adds them to the gradient.
 #include "../../include/molearn_b200.h"
 #include "topology.hpp"
 
@@ -42,15 +46,17 @@
 // ------------------------------------------------------------------------------------------
 constexpr int BT = 256;          // bonded: threads per CTA
 constexpr int RB = 2, RA = 2, RT = 2;  // bonded: max bonds / angles / torsions per thread
+constexpr int PF = 4;            // bonded: coordinate elements staged per thread (3*(own+halo) <= PF*BT)
 constexpr int NF = 4;            // torsion Fourier orders kept (ff14SB periods are 1..4)
 constexpr int NB_T = 128;        // non-bonded tile edge (atoms)
 constexpr int NB_NI = 4;         // i-atoms per lane
 constexpr int NB_WARPS = 4;      // warps per CTA, one work item each
 #ifndef NB_MINB
-#define NB_MINB 3
+#define NB_MINB 4
 #endif
 constexpr float LJ_K = 1.9f, C_K = 0.4f;  // warp thresholds, torch_protein_energy.py:233-234
 constexpr float CLAMP = 0.999999f;        // acos clamp, :289
+constexpr size_t BONDED_SMEM_CAP = 100 * 1024;  // keep two CTAs per SM
 
 struct BondRec { uint32_t ij, slots; float r0, k; };                       // 16 B
 struct AngleRec { uint32_t ij, k, s_ij, s_k; float th0, kf, pad0, pad1; }; // 32 B
@@ -60,8 +66,8 @@ constexpr uint32_t OWNER = 0x8000u;  // bit 15 of the first local index: this ti
 
 struct BTile {
     int a0, n_own, n_halo, halo_off;
-    int bond_off, n_bond, angle_off, n_angle, tors_off, n_tors;
-    int csr_off, n_slots;
+    int bond_off, n_bond, angle_off, n_angle, tors_off, n_tors;  // counts are padded to multiples of 32
+    int cnt_off, pad;
 };
 
 struct mlp_energy {
@@ -69,27 +75,27 @@ struct mlp_energy {
     uint32_t nb_mode = 0;
     int N = 0, Npad = 0;
     // bonded
-    int n_tiles = 0, max_slots = 0, max_atoms = 0;
+    int n_tiles = 0, tile_atoms = 0, slot_stride = 0, max_cnt = 0, max_atoms = 0;
     BTile* d_tiles = nullptr;
     int* d_halo = nullptr;
     BondRec* d_bonds = nullptr;
     AngleRec* d_angles = nullptr;
     TorsRec* d_tors = nullptr;
-    int* d_csr = nullptr;
+    int* d_cnt = nullptr;
     size_t bonded_smem = 0;
     // non-bonded
     int n_nbt = 0;                 // tiles per edge
     int n_pairs = 0, n_masked = 0; // tile pairs (masked ones first)
     int2* d_pairs = nullptr;       // (I,J)
-    uint32_t* d_masks = nullptr;   // [n_masked][128][4]
+    uint32_t* d_masks = nullptr;   // [n_masked][32 groups][32 lanes] uint16 pair masks
     float* d_q = nullptr;          // [Npad]
     float2* d_par = nullptr;       // [Npad] (R/2, sqrt(12 eps))
-    float* d_ones = nullptr;       // [4] default weights
+    int* d_red_off = nullptr;      // [n_nbt+1] per tile: range in d_red_list
+    int* d_red_list = nullptr;     // entries pair*2 + side (0: the tile is the pair's I, 1: its J)
     int last_launches = 0;
     int sm_count = 148;
     // optional per-kernel timing (mlp_energy_profile): events on the launching stream
     bool profile = false;
-    cudaEvent_t ev[8] = {};
     std::vector<std::array<cudaEvent_t, 2>> pending[4];  // per kernel: (start, stop) pairs not read yet
     double prof_ms[4] = {0, 0, 0, 0};
     long prof_n[4] = {0, 0, 0, 0};
@@ -122,6 +128,17 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// 1/sqrt(x) to ~1 ulp: MUFU + one Newton step (the bare MUFU is 2 ulp; (d - r0) and cos(n phi) magnify it)
+__device__ __forceinline__ float rsqrt_nr(float x) {
+    float y = rsqrt_fast(x);
+    float h = 0.5f * x * y;
+    return y * fmaf(-h, y, 1.5f);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -132,46 +149,48 @@ __device__ __forceinline__ float warp_sum(float v) {
 // bonded kernel
 // ------------------------------------------------------------------------------------------
 // E = K (|ri-rj| - r0)^2                      (torch_protein_energy.py:282-284)
-__device__ __forceinline__ float bond_term(const float4* sc, float4* slots, const BondRec& r, float w, bool grad, float& e) {
+template <bool GRAD>
+__device__ __forceinline__ void bond_term(const float4* sc, float4* slots, const BondRec& r, float w, float& e) {
     const uint32_t i = r.ij & 0x7fffu, j = r.ij >> 16;
     float3 v = f3(sc[i]) - f3(sc[j]);
     float d2 = dot(v, v);
-    float d = sqrtf(d2);
+    float inv = d2 > 0.f ? rsqrt_nr(d2) : 0.f;   // autograd: d|v|/dv = 0 at v = 0
+    float d = d2 * inv;
+    d = d2 != d2 ? d2 : d;
     float dl = d - r.r0;
-    float en = r.k * dl * dl;
-    if (r.ij & OWNER) e += en;
-    if (grad) {
-        float c = d > 0.f ? w * 2.f * r.k * dl / d : 0.f;  // autograd: d|v|/dv = 0 at v = 0
-        float3 g = c * v;
+    float kdl = r.k * dl;
+    if (r.ij & OWNER) e = fmaf(kdl, dl, e);
+    if (GRAD) {
+        float3 g = (2.f * w * kdl * inv) * v;
         slots[r.slots & 0xffffu] = f4(g);
         slots[r.slots >> 16] = f4(-1.f * g);
     }
-    return en;
 }
 
 // theta = acos(clamp(v1.v2/(|v1||v2|))), E = K (theta-theta0)^2      (:286-293)
-__device__ __forceinline__ void angle_term(const float4* sc, float4* slots, const AngleRec& r, float w, bool grad, float& e) {
+template <bool GRAD>
+__device__ __forceinline__ void angle_term(const float4* sc, float4* slots, const AngleRec& r, float w, float& e) {
     const uint32_t i = r.ij & 0x7fffu, j = r.ij >> 16, k = r.k;
     float3 rj = f3(sc[j]);
     float3 v1 = f3(sc[i]) - rj, v2 = f3(sc[k]) - rj;
     float n1 = dot(v1, v1), n2 = dot(v2, v2);
-    float inv12 = 1.0f / (sqrtf(n1) * sqrtf(n2));
-    float c = dot(v1, v2) * inv12;
+    float c = dot(v1, v2) * rsqrt_nr(n1 * n2);
     float cc = fminf(fmaxf(c, -CLAMP), CLAMP);
     float th = acosf(cc);
     if (c != c) th = c;  // NaN propagates (fminf/fmaxf would swallow it)
     float dt = th - r.th0;
-    if (r.ij & OWNER) e += r.kf * dt * dt;
-    if (grad) {
+    float kdt = r.kf * dt;
+    if (r.ij & OWNER) e = fmaf(kdt, dt, e);
+    if (GRAD) {
         // dtheta/dv1 = v1 x (v1 x v2) / (|v1|^2 |v1 x v2|), dtheta/dv2 = -v2 x (v1 x v2) / (|v2|^2 |v1 x v2|):
         // the cross-product form of -1/sqrt(1-c^2) * dc/dv, which does not cancel near c = +-1.
         // torch.clamp passes no gradient outside the clamp, so the term is dropped there.
         float3 n = cross(v1, v2);
         float nn = dot(n, n);
-        float coef = (c > -CLAMP && c < CLAMP) ? w * 2.f * r.kf * dt * rsqrtf(nn) : 0.f;
+        float coef = (c > -CLAMP && c < CLAMP) ? 2.f * w * kdt * rsqrt_fast(nn) : 0.f;
         if (c != c) coef = c;
-        float3 gi = (coef / n1) * cross(v1, n);
-        float3 gk = (-coef / n2) * cross(v2, n);
+        float3 gi = (coef * rcp_fast(n1)) * cross(v1, n);
+        float3 gk = (-coef * rcp_fast(n2)) * cross(v2, n);
         slots[r.s_ij & 0xffffu] = f4(gi);
         slots[r.s_k] = f4(gk);
         slots[r.s_ij >> 16] = f4(-1.f * (gi + gk));
@@ -180,33 +199,36 @@ __device__ __forceinline__ void angle_term(const float4* sc, float4* slots, cons
 
 // phi = atan2(b2.(c32 x c12), |b2| c12.c32), E = sum_p (V/f)(1+cos(n phi - gamma))   (:295-304)
 // evaluated as a Fourier series in (cos phi, sin phi) - no atan2 / cos calls.
-__device__ __forceinline__ void torsion_term(const float4* sc, float4* slots, const TorsRec& r, float w, bool grad, float& e) {
+template <bool GRAD>
+__device__ __forceinline__ void torsion_term(const float4* sc, float4* slots, const TorsRec& r, float w, float& e) {
     const uint32_t i = r.ij & 0x7fffu, j = r.ij >> 16, k = r.kl & 0xffffu, l = r.kl >> 16;
     float3 rj = f3(sc[j]), rk = f3(sc[k]);
     float3 F = f3(sc[i]) - rj, G = rj - rk, H = f3(sc[l]) - rk;
     float3 A = cross(F, G), B = cross(H, G);
     float G2 = dot(G, G);
-    float Gn = sqrtf(G2);
+    float iG = rsqrt_nr(G2);
+    float Gn = G2 * iG;
     float X = dot(A, B), Y = -Gn * dot(B, F);
-    float rho2 = X * X + Y * Y;
-    float irho = rsqrtf(rho2);
-    // atan2(0,0) = 0 in the reference's forward
-    float c1 = rho2 > 0.f ? X * irho : 1.f, s1 = rho2 > 0.f ? Y * irho : 0.f;
+    float rho2 = fmaf(X, X, Y * Y);
+    float irho = rsqrt_nr(rho2);
+    // atan2(0,0) = 0 in the reference's forward; NaN/inf fall through and propagate
+    float c1 = rho2 == 0.f ? 1.f : X * irho, s1 = rho2 == 0.f ? 0.f : Y * irho;
     float cn = c1, sn = s1;
     float en = r.c0, de = 0.f;  // de = dE/dphi
 #pragma unroll
     for (int n = 1; n <= NF; ++n) {
         en = fmaf(r.cg[n - 1], cn, fmaf(r.sg[n - 1], sn, en));
-        de = fmaf((float)n, fmaf(r.sg[n - 1], cn, -r.cg[n - 1] * sn), de);
-        float c2 = cn * c1 - sn * s1;
-        sn = fmaf(sn, c1, cn * s1);
-        cn = c2;
+        if (GRAD) de = fmaf((float)n, fmaf(r.sg[n - 1], cn, -r.cg[n - 1] * sn), de);
+        if (n < NF) {
+            float c2 = fmaf(cn, c1, -sn * s1);
+            sn = fmaf(sn, c1, cn * s1);
+            cn = c2;
+        }
     }
     if (r.ij & OWNER) e += en;
-    if (grad) {
+    if (GRAD) {
         de *= w;
-        float A2 = dot(A, A), B2 = dot(B, B);
-        float iA2 = 1.f / A2, iB2 = 1.f / B2, iG = 1.f / Gn;
+        float iA2 = rcp_fast(dot(A, A)), iB2 = rcp_fast(dot(B, B));
         float3 gi = (-de * Gn * iA2) * A;
         float3 gl = (de * Gn * iB2) * B;
         float fa = de * dot(F, G) * iA2 * iG, hb = de * dot(H, G) * iB2 * iG;
@@ -221,136 +243,126 @@ __device__ __forceinline__ void torsion_term(const float4* sc, float4* slots, co
 template <bool GRAD>
 __global__ void __launch_bounds__(BT, 2)
 bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, const BondRec* __restrict__ bonds,
-              const AngleRec* __restrict__ angles, const TorsRec* __restrict__ tors, const int* __restrict__ csr,
+              const AngleRec* __restrict__ angles, const TorsRec* __restrict__ tors, const int* __restrict__ cnts,
               const float* __restrict__ x, long sxb, long sxc, long sxn,
               float* __restrict__ grad, long sgb, long sgc, long sgn,
-              const float* __restrict__ weights, double* __restrict__ acc,
-              int B, int conf_per_cta, uint32_t term_mask, int accumulate, int max_atoms) {
+              const float* __restrict__ weights, float* __restrict__ e_part /* [B][n_tiles][3] or null */,
+              int B, int conf_per_cta, uint32_t term_mask, int accumulate, int max_atoms, int stride, int max_cnt) {
     extern __shared__ float4 smem[];
     float4* sc = smem;                 // [max_atoms] coordinates of own + halo atoms
-    float4* slots = smem + max_atoms;  // [n_slots + 1] gradient slots (last = dump)
-    __shared__ float s_e[3];
+    float4* slots = smem + max_atoms;  // [max_cnt*stride + 1] gradient slots, slot (atom a, k) at k*stride + a; last = dump
+    __shared__ float s_w[BT / 32][3];
 
     const BTile t = tiles[blockIdx.x];
-    const int tid = threadIdx.x;
-    const int n_at = t.n_own + t.n_halo;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wbase = tid & ~31;
 
-    // term records -> registers, once per CTA
+    // term records -> registers, once per CTA (lists are padded to whole warps with inert terms)
     BondRec rb[RB];
     AngleRec ra[RA];
     TorsRec rt[RT];
+    bool ab[RB], aa[RA], at[RT];   // warp-uniform activity flags
 #pragma unroll
-    for (int r = 0; r < RB; ++r)
-        if (tid + r * BT < t.n_bond) rb[r] = bonds[t.bond_off + tid + r * BT];
+    for (int r = 0; r < RB; ++r) { ab[r] = wbase + r * BT < t.n_bond; if (ab[r]) rb[r] = bonds[t.bond_off + tid + r * BT]; }
 #pragma unroll
-    for (int r = 0; r < RA; ++r)
-        if (tid + r * BT < t.n_angle) ra[r] = angles[t.angle_off + tid + r * BT];
+    for (int r = 0; r < RA; ++r) { aa[r] = wbase + r * BT < t.n_angle; if (aa[r]) ra[r] = angles[t.angle_off + tid + r * BT]; }
 #pragma unroll
-    for (int r = 0; r < RT; ++r)
-        if (tid + r * BT < t.n_tors) rt[r] = tors[t.tors_off + tid + r * BT];
-    int s_lo = 0, s_hi = 0;
-    if (GRAD && tid < t.n_own) { s_lo = csr[t.csr_off + tid]; s_hi = csr[t.csr_off + tid + 1]; }
+    for (int r = 0; r < RT; ++r) { at[r] = wbase + r * BT < t.n_tors; if (at[r]) rt[r] = tors[t.tors_off + tid + r * BT]; }
+    const int my_cnt = (GRAD && tid < t.n_own) ? cnts[t.cnt_off + tid] : 0;
 
-    // element e of the tile's coordinate block -> (local atom, component, global atom)
-    const int n_el = 3 * n_at;
-    const bool aos = (sxc == 1);
-    auto elem = [&](int e, int& la, int& c) {
-        if (e < 3 * t.n_own) {
-            if (aos) { la = e / 3; c = e - 3 * la; } else { c = e / t.n_own; la = e - c * t.n_own; }
-        } else {
-            int h = e - 3 * t.n_own;
-            la = t.n_own + h / 3; c = h - 3 * (h / 3);
-        }
-    };
-    auto gatom = [&](int la) { return la < t.n_own ? t.a0 + la : halo[t.halo_off + la - t.n_own]; };
-
-    const int b0 = blockIdx.y * conf_per_cta;
-    const int b1 = min(B, b0 + conf_per_cta);
-    constexpr int PF = 4;  // prefetch registers: 3*(256+halo)/256 <= 4 elements per thread
-    float pf[PF];
-    auto prefetch = [&](int b) {
+    // coordinate staging plan: element e = tid + q*BT of the tile's 3*(own+halo) floats
+    long goff[PF];
+    int sidx[PF];
+    {
+        const int n_el = 3 * (t.n_own + t.n_halo);
+        const bool aos = (sxc == 1);
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
             int e = tid + q * BT;
+            sidx[q] = -1;
+            goff[q] = 0;
             if (e < n_el) {
-                int la, c; elem(e, la, c);
-                pf[q] = x[(long)b * sxb + c * sxc + (long)gatom(la) * sxn];
+                int la, c;
+                if (e < 3 * t.n_own) {
+                    if (aos) { la = e / 3; c = e - 3 * la; } else { c = e / t.n_own; la = e - c * t.n_own; }
+                } else {
+                    int h = e - 3 * t.n_own;
+                    la = t.n_own + h / 3; c = h - 3 * (h / 3);
+                }
+                int ga = la < t.n_own ? t.a0 + la : halo[t.halo_off + la - t.n_own];
+                goff[q] = c * sxc + (long)ga * sxn;
+                sidx[q] = 4 * la + c;
             }
         }
+    }
+    float* scf = reinterpret_cast<float*>(sc);
+
+    const int b0 = blockIdx.y * conf_per_cta;
+    const int b1 = min(B, b0 + conf_per_cta);
+    float pf[PF];
+    auto prefetch = [&](int b) {
+        const float* xb = x + (long)b * sxb;
+#pragma unroll
+        for (int q = 0; q < PF; ++q) if (sidx[q] >= 0) pf[q] = xb[goff[q]];
     };
+    const bool do_b = term_mask & MLP_TERM_BOND, do_a = term_mask & MLP_TERM_ANGLE, do_t = term_mask & MLP_TERM_TORSION;
 
     if (b0 < b1) prefetch(b0);
     for (int b = b0; b < b1; ++b) {
         float wb = 1.f, wa = 1.f, wt = 1.f;
         if (weights) { wb = weights[4 * b]; wa = weights[4 * b + 1]; wt = weights[4 * b + 2]; }
-        const bool do_b = term_mask & MLP_TERM_BOND, do_a = term_mask & MLP_TERM_ANGLE, do_t = term_mask & MLP_TERM_TORSION;
-        if (GRAD && accumulate && !acc && (!do_b || wb == 0.f) && (!do_a || wa == 0.f) && (!do_t || wt == 0.f)) {
+        if (GRAD && accumulate && !e_part && (!do_b || wb == 0.f) && (!do_a || wa == 0.f) && (!do_t || wt == 0.f)) {
             // backward correction with nothing to add for this conformation (CTA-uniform)
             if (b + 1 < b1) prefetch(b + 1);
             continue;
         }
-        // stage coordinates (previous iteration's term phase is over: all threads passed the sync below)
+        // stage coordinates (the previous iteration's term phase is over: everybody passed its second barrier)
 #pragma unroll
-        for (int q = 0; q < PF; ++q) {
-            int e = tid + q * BT;
-            if (e < n_el) { int la, c; elem(e, la, c); reinterpret_cast<float*>(&sc[la])[c] = pf[q]; }
-        }
-        for (int e = tid + PF * BT; e < n_el; e += BT) {
-            int la, c; elem(e, la, c);
-            reinterpret_cast<float*>(&sc[la])[c] = x[(long)b * sxb + c * sxc + (long)gatom(la) * sxn];
-        }
-        if (tid < 3) s_e[tid] = 0.f;
+        for (int q = 0; q < PF; ++q) if (sidx[q] >= 0) scf[sidx[q]] = pf[q];
+        if (GRAD && term_mask != MLP_TERM_BONDED)
+            for (int s = tid; s < max_cnt * stride; s += BT) slots[s] = make_float4(0.f, 0.f, 0.f, 0.f);  // rare: a term type is off
         __syncthreads();
         if (b + 1 < b1) prefetch(b + 1);
 
         float eb = 0.f, ea = 0.f, et = 0.f;
         if (do_b) {
 #pragma unroll
-            for (int r = 0; r < RB; ++r)
-                if (tid + r * BT < t.n_bond) bond_term(sc, slots, rb[r], wb, GRAD, eb);
+            for (int r = 0; r < RB; ++r) if (ab[r]) bond_term<GRAD>(sc, slots, rb[r], wb, eb);
         }
         if (do_a) {
 #pragma unroll
-            for (int r = 0; r < RA; ++r)
-                if (tid + r * BT < t.n_angle) angle_term(sc, slots, ra[r], wa, GRAD, ea);
+            for (int r = 0; r < RA; ++r) if (aa[r]) angle_term<GRAD>(sc, slots, ra[r], wa, ea);
         }
         if (do_t) {
 #pragma unroll
-            for (int r = 0; r < RT; ++r)
-                if (tid + r * BT < t.n_tors) torsion_term(sc, slots, rt[r], wt, GRAD, et);
+            for (int r = 0; r < RT; ++r) if (at[r]) torsion_term<GRAD>(sc, slots, rt[r], wt, et);
         }
-        if (GRAD && term_mask != MLP_TERM_BONDED) {
-            // a masked-out term type leaves its slots unwritten: zero them
-            // (rare path: backward corrections with a subset of terms)
-#pragma unroll
-            for (int r = 0; r < RB; ++r)
-                if (!do_b && tid + r * BT < t.n_bond) { slots[rb[r].slots & 0xffffu] = make_float4(0, 0, 0, 0); slots[rb[r].slots >> 16] = make_float4(0, 0, 0, 0); }
-#pragma unroll
-            for (int r = 0; r < RA; ++r)
-                if (!do_a && tid + r * BT < t.n_angle) {
-                    slots[ra[r].s_ij & 0xffffu] = make_float4(0, 0, 0, 0); slots[ra[r].s_ij >> 16] = make_float4(0, 0, 0, 0);
-                    slots[ra[r].s_k] = make_float4(0, 0, 0, 0);
-                }
-#pragma unroll
-            for (int r = 0; r < RT; ++r)
-                if (!do_t && tid + r * BT < t.n_tors) {
-                    slots[rt[r].s_ij & 0xffffu] = make_float4(0, 0, 0, 0); slots[rt[r].s_ij >> 16] = make_float4(0, 0, 0, 0);
-                    slots[rt[r].s_kl & 0xffffu] = make_float4(0, 0, 0, 0); slots[rt[r].s_kl >> 16] = make_float4(0, 0, 0, 0);
-                }
+        if (e_part) {
+            eb = warp_sum(eb); ea = warp_sum(ea); et = warp_sum(et);
+            if (lane == 0) { s_w[warp][0] = eb; s_w[warp][1] = ea; s_w[warp][2] = et; }
         }
-        eb = warp_sum(eb); ea = warp_sum(ea); et = warp_sum(et);
-        if ((tid & 31) == 0) { atomicAdd(&s_e[0], eb); atomicAdd(&s_e[1], ea); atomicAdd(&s_e[2], et); }
         __syncthreads();
-        if (tid < 3 && acc) atomicAdd(&acc[4 * (long)b + tid], (double)s_e[tid]);
+        if (e_part && tid < 3) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < BT / 32; ++k) s += s_w[k][tid];     // fixed order: reproducible
+            e_part[((long)b * gridDim.x + blockIdx.x) * 3 + tid] = s;
+        }
         if (GRAD && tid < t.n_own) {
             float gx = 0.f, gy = 0.f, gz = 0.f;
-            for (int s = s_lo; s < s_hi; ++s) { float4 v = slots[s]; gx += v.x; gy += v.y; gz += v.z; }
+            const float4* col = slots + tid;
+            int k = 0;
+            for (; k + 4 <= my_cnt; k += 4) {
+                float4 v0 = col[k * stride], v1 = col[(k + 1) * stride], v2 = col[(k + 2) * stride], v3 = col[(k + 3) * stride];
+                gx += (v0.x + v1.x) + (v2.x + v3.x); gy += (v0.y + v1.y) + (v2.y + v3.y); gz += (v0.z + v1.z) + (v2.z + v3.z);
+            }
+            for (; k < my_cnt; ++k) { float4 v = col[k * stride]; gx += v.x; gy += v.y; gz += v.z; }
             float* g = grad + (long)b * sgb + (long)(t.a0 + tid) * sgn;
             if (accumulate) { g[0] += gx; g[sgc] += gy; g[2 * sgc] += gz; }
             else { g[0] = gx; g[sgc] = gy; g[2 * sgc] = gz; }
         }
-        // next iteration's coordinate staging only touches sc (term phase done); its slot
-        // writes happen after the next __syncthreads, i.e. after every gather above.
+        // the next iteration's staging only touches sc (term phase done); its slot writes happen after the
+        // next barrier, i.e. after every gather above.
     }
 }
 
@@ -361,6 +373,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
 // zero charge / epsilon so that they contribute exactly 0 without any test in the pair loop.
 __global__ void nb_pack_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float* __restrict__ q,
                                float4* __restrict__ xq, int N, int Npad, int B) {
+    // (conformations whose upstream NB weight is 0 are packed too: 28 B per atom, not worth a test)
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)B * Npad) return;
     int b = (int)(idx / Npad), n = (int)(idx - (long)b * Npad);
@@ -430,12 +443,13 @@ __device__ __noinline__ float3 nb_pair_fix(float r2, float Rij, float e12, float
 }
 
 // One micro-tile: NB_NI i-atoms (registers) x 4 j-atoms, fast path with clamped distance.
-// m16: bit (4a+b) = pair allowed (MASKED tiles).  Returns the smallest true r^2 of the allowed pairs.
+// m16: bit (4a+b) = pair allowed (MASKED tiles).  Returns true if any allowed pair is closer than
+// sqrt(NB_THR2) or not comparable (NaN coordinates) - the caller then runs the exact correction.
 template <bool MASKED, bool FULL>
-__device__ __forceinline__ float nb_micro(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
+__device__ __forceinline__ bool nb_micro(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
                                           const float2 (&pj)[4], uint32_t m16,
                                           float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
-    float rmin = 1e30f;
+    bool close = false;
 #pragma unroll
     for (int a = 0; a < NB_NI; ++a) {
 #pragma unroll
@@ -451,13 +465,13 @@ __device__ __forceinline__ float nb_micro(const float4 (&xi)[NB_NI], const float
                 e12 = on ? e12 : 0.f;
                 qq = on ? qq : 0.f;
             }
-            rmin = fminf(rmin, r2);
+            close = close || !(r2 >= NB_THR2);
             float s = nb_pair_fast<FULL>(fmaxf(r2, NB_THR2), Rij, e12, qq, Sl, Sc);
             Fi[a].x = fmaf(s, dx, Fi[a].x); Fi[a].y = fmaf(s, dy, Fi[a].y); Fi[a].z = fmaf(s, dz, Fi[a].z);
             Fj[b].x = fmaf(s, dx, Fj[b].x); Fj[b].y = fmaf(s, dy, Fj[b].y); Fj[b].z = fmaf(s, dz, Fj[b].z);
         }
     }
-    return rmin;
+    return close;
 }
 
 // Correction pass over a micro-tile that holds at least one pair closer than sqrt(NB_THR2).
@@ -499,13 +513,13 @@ __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const fl
 // One warp = one (conformation, tile pair).  Lane L owns i-atoms i0+L+32a (a<4) for the whole
 // tile; the 32 groups of 4 j-atoms rotate through the lanes (lane L works on group (L+r)%32 at
 // step r) together with their force accumulators, so Newton's third law costs 12 shuffles per
-// 16 pairs and no reduction.
+// 16 pairs and no reduction.  Output: partial forces of the item's 128 i-atoms and 128 j-atoms
+// ([6][128] floats: -Fi xyz, +Fj xyz) and its energy - no atomics.
 template <bool GRAD, bool FULL>
 __global__ void __launch_bounds__(NB_WARPS * 32, NB_MINB)
 nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const int2* __restrict__ pairs,
-          const uint32_t* __restrict__ masks, int n_pairs, int n_masked, int Npad, int N, int B,
-          float* __restrict__ grad, long sgb, long sgc, long sgn, const float* __restrict__ weights,
-          double* __restrict__ acc) {
+          const uint32_t* __restrict__ masks, int n_pairs, int n_masked, int Npad, int B,
+          float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
     // j tile, group-minor: atom 4g+b lives at [b*32+g] so that lanes (different g) never conflict
     __shared__ float4 s_xj[NB_WARPS][NB_T];
     __shared__ float2 s_pj[NB_WARPS][NB_T];
@@ -514,8 +528,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     const long item = (long)blockIdx.x * NB_WARPS + warp;
     if (item >= (long)B * n_pairs) return;
     const int b = (int)(item / n_pairs), p = (int)(item - (long)b * n_pairs);
-    const float wnb = weights ? weights[4 * b + 3] : 1.f;
-    if (weights && wnb == 0.f && acc == nullptr) return;  // backward correction with nothing to add
+    if (weights && !e_part && weights[4 * b + 3] == 0.f) return;  // backward correction with nothing to add (nb_reduce skips it too)
     const int2 IJ = pairs[p];
     const int i0 = IJ.x * NB_T, j0 = IJ.y * NB_T;
     const float4* xb = xq + (long)b * Npad;
@@ -561,11 +574,11 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
         for (int q = 0; q < 4; ++q) { xj[q] = s_xj[warp][q * 32 + g]; pj[q] = s_pj[warp][q * 32 + g]; }
         if (masked) {
             const uint32_t m16 = sm16[g * 32 + lane];
-            float rmin = nb_micro<true, FULL>(xi, pi, xj, pj, m16, Fi, Fj, Sl, Sc);
-            if (!(rmin >= NB_THR2)) nb_micro_fix<true, FULL>(xi, pi, xj, pj, m16, Fi, Fj, Sl, Sc);
+            if (nb_micro<true, FULL>(xi, pi, xj, pj, m16, Fi, Fj, Sl, Sc))
+                nb_micro_fix<true, FULL>(xi, pi, xj, pj, m16, Fi, Fj, Sl, Sc);
         } else {
-            float rmin = nb_micro<false, FULL>(xi, pi, xj, pj, 0xffffu, Fi, Fj, Sl, Sc);
-            if (!(rmin >= NB_THR2)) nb_micro_fix<false, FULL>(xi, pi, xj, pj, 0xffffu, Fi, Fj, Sl, Sc);
+            if (nb_micro<false, FULL>(xi, pi, xj, pj, 0xffffu, Fi, Fj, Sl, Sc))
+                nb_micro_fix<false, FULL>(xi, pi, xj, pj, 0xffffu, Fi, Fj, Sl, Sc);
         }
         if (GRAD) {
 #pragma unroll
@@ -579,29 +592,48 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     if (GRAD) {
         // after 32 rotations lane L holds the finished forces of group L (atoms j0+4L+q);
         // grad_i = -sum s*(ri-rj), grad_j = +sum s*(ri-rj)   (s = -(dE/dd)/d)
-        float* gb = grad + (long)b * sgb;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int ja = j0 + 4 * lane + q;
-            if (ja < N) {
-                float* g = gb + (long)ja * sgn;
-                atomicAdd(g, wnb * Fj[q].x); atomicAdd(g + sgc, wnb * Fj[q].y); atomicAdd(g + 2 * sgc, wnb * Fj[q].z);
-            }
-        }
+        float* out = fpart + item * (6 * NB_T);
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) {
-            int ia = i0 + lane + 32 * a;
-            if (ia < N) {
-                float* g = gb + (long)ia * sgn;
-                atomicAdd(g, -wnb * Fi[a].x); atomicAdd(g + sgc, -wnb * Fi[a].y); atomicAdd(g + 2 * sgc, -wnb * Fi[a].z);
-            }
+            out[0 * NB_T + lane + 32 * a] = -Fi[a].x;
+            out[1 * NB_T + lane + 32 * a] = -Fi[a].y;
+            out[2 * NB_T + lane + 32 * a] = -Fi[a].z;
         }
+        reinterpret_cast<float4*>(out + 3 * NB_T)[lane] = make_float4(Fj[0].x, Fj[1].x, Fj[2].x, Fj[3].x);
+        reinterpret_cast<float4*>(out + 4 * NB_T)[lane] = make_float4(Fj[0].y, Fj[1].y, Fj[2].y, Fj[3].y);
+        reinterpret_cast<float4*>(out + 5 * NB_T)[lane] = make_float4(Fj[0].z, Fj[1].z, Fj[2].z, Fj[3].z);
     }
-    if (acc) {
+    if (e_part) {
         // E = sum_lj12/12 + sum_coulomb
         double e = (double)warp_sum(Sl) * (1.0 / 12.0) + (double)warp_sum(Sc);
-        if (lane == 0) atomicAdd(&acc[4 * (long)b + 3], e);
+        if (lane == 0) e_part[item] = e;
     }
+}
+
+// grad[b, n] (+)= w_nb[b] * (sum of the partial forces of every tile pair in n's tile row / column),
+// summed in list order: reproducible.
+__global__ void __launch_bounds__(NB_T)
+nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_off, const int* __restrict__ red_list,
+                 int n_pairs, int N, float* __restrict__ grad, long sgb, long sgc, long sgn,
+                 const float* __restrict__ weights, int accumulate, int skip_zero_weight) {
+    const int T = blockIdx.x, b = blockIdx.y, l = threadIdx.x;
+    const int n = T * NB_T + l;
+    const float w = weights ? weights[4 * b + 3] : 1.f;
+    if (n >= N) return;
+    float* g = grad + (long)b * sgb + (long)n * sgn;
+    if (skip_zero_weight && w == 0.f) {          // nb_kernel wrote no partials for this conformation
+        if (!accumulate) { g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
+        return;
+    }
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    const float* base = fpart + (long)b * n_pairs * (6 * NB_T) + l;
+    for (int k = red_off[T]; k < red_off[T + 1]; ++k) {
+        const int e = red_list[k];
+        const float* p = base + (long)(e >> 1) * (6 * NB_T) + (e & 1) * (3 * NB_T);
+        sx += p[0]; sy += p[NB_T]; sz += p[2 * NB_T];
+    }
+    if (accumulate) { g[0] = fmaf(w, sx, g[0]); g[sgc] = fmaf(w, sy, g[sgc]); g[2 * sgc] = fmaf(w, sz, g[2 * sgc]); }
+    else { g[0] = w * sx; g[sgc] = w * sy; g[2 * sgc] = w * sz; }
 }
 
 __global__ void zero_grad_kernel(float* __restrict__ grad, long sgb, long sgc, long sgn, int N, int B) {
@@ -613,9 +645,28 @@ __global__ void zero_grad_kernel(float* __restrict__ grad, long sgb, long sgc, l
     grad[(long)b * sgb + c * sgc + (long)n * sgn] = 0.f;
 }
 
-__global__ void finalize_kernel(const double* __restrict__ acc, float* __restrict__ energies, int n) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < n) energies[idx] = (float)acc[idx];
+// energies[b] = (sum over bonded tiles, sum over NB tile pairs), fixed order, fp64 accumulation
+__global__ void __launch_bounds__(128)
+finalize_kernel(const float* __restrict__ e_bonded, int n_tiles, const double* __restrict__ e_nb, int n_pairs,
+                float* __restrict__ energies, uint32_t term_mask) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ double red[128];
+    double s = 0.0;
+    if (term_mask & MLP_TERM_NB)
+        for (int p = tid; p < n_pairs; p += 128) s += e_nb[(long)b * n_pairs + p];
+    red[tid] = s;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) energies[4 * b + 3] = (float)red[0];
+    if (tid < 3) {
+        double v = 0.0;
+        if (term_mask & (1u << tid))
+            for (int t = 0; t < n_tiles; ++t) v += (double)e_bonded[((long)b * n_tiles + t) * 3 + tid];
+        energies[4 * b + tid] = (float)v;
+    }
 }
 
 // RMSD of x*scale+shift to K targets: out[b,k] = sqrt(sum_{n,c} d^2 / N)
@@ -654,8 +705,9 @@ template <class T> int upload(mlp_energy* E, T** dst, const std::vector<T>& v) {
     return MLP_OK;
 }
 
-struct Term { int type; int idx; };  // type 0 bond, 1 angle, 2 torsion
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// returns 1 if the tile size does not fit the kernel's static limits (the caller retries smaller)
 int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
     const int N = T.n_atoms;
     const int nb = (int)T.bonds.size() / 2, na = (int)T.angles.size() / 3, nt = (int)T.torsions.size() / 4, P = T.P;
@@ -687,120 +739,125 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
         for (int n = 0; n < NF; ++n) { t_coef[k][1 + n] = (float)cg[n]; t_coef[k][1 + NF + n] = (float)sg[n]; }
     }
 
-    std::vector<BTile> tiles;
-    std::vector<int> halo_all, csr_all;
-    std::vector<BondRec> bonds_all;
-    std::vector<AngleRec> angles_all;
-    std::vector<TorsRec> tors_all;
-    // per-atom incident terms
-    std::vector<std::vector<Term>> inc(N);
+    // per-atom incident (term, role) lists: bonds, then angles, then torsions with a non-zero series
+    struct Inc { int type, idx, role; };
+    std::vector<std::vector<Inc>> inc(N);
     auto touch = [&](int type, int idx, const int32_t* a, int n) {
-        for (int r = 0; r < n; ++r) {
-            bool dup = false;
-            for (int q = 0; q < r; ++q) dup = dup || a[q] == a[r];
-            if (!dup) inc[a[r]].push_back({type, idx});
-        }
+        for (int r = 0; r < n; ++r) inc[a[r]].push_back({type, idx, r});
     };
     for (int k = 0; k < nb; ++k) touch(0, k, &T.bonds[2 * k], 2);
     for (int k = 0; k < na; ++k) touch(1, k, &T.angles[3 * k], 3);
     for (int k = 0; k < nt; ++k) if (t_live[k]) touch(2, k, &T.torsions[4 * k], 4);
+    int max_cnt = 1;
+    for (int a = 0; a < N; ++a) max_cnt = std::max(max_cnt, (int)inc[a].size());
+    const int stride = (std::min(tile_atoms, std::max(N, 1)) + 31) & ~31;
+    if ((size_t)max_cnt * stride + 1 >= 0xffff) return 1;
+    const uint32_t dump = (uint32_t)(max_cnt * stride);
 
-    int max_slots = 0, max_atoms = 0;
+    std::vector<BTile> tiles;
+    std::vector<int> halo_all, cnt_all;
+    std::vector<BondRec> bonds_all;
+    std::vector<AngleRec> angles_all;
+    std::vector<TorsRec> tors_all;
+    int max_atoms = 1;
     for (int a0 = 0; a0 < N; a0 += tile_atoms) {
         const int n_own = std::min(tile_atoms, N - a0);
         BTile bt{};
         bt.a0 = a0; bt.n_own = n_own;
-        // unique terms of the tile, in (type, index) order
         std::vector<int> tb, ta, tt;
         for (int a = a0; a < a0 + n_own; ++a)
-            for (const Term& tm : inc[a]) (tm.type == 0 ? tb : tm.type == 1 ? ta : tt).push_back(tm.idx);
+            for (const Inc& tm : inc[a]) (tm.type == 0 ? tb : tm.type == 1 ? ta : tt).push_back(tm.idx);
         auto uniq = [](std::vector<int>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
         uniq(tb); uniq(ta); uniq(tt);
-        if ((int)tb.size() > RB * BT || (int)ta.size() > RA * BT || (int)tt.size() > RT * BT) return 1;  // tile too dense
-        // halo
+        auto pad32 = [](size_t n) { return (int)((n + 31) & ~(size_t)31); };
+        if (pad32(tb.size()) > RB * BT || pad32(ta.size()) > RA * BT || pad32(tt.size()) > RT * BT) return 1;
         std::vector<int> halo;
         auto need = [&](int a) { if (a < a0 || a >= a0 + n_own) halo.push_back(a); };
         for (int k : tb) for (int r = 0; r < 2; ++r) need(T.bonds[2 * k + r]);
         for (int k : ta) for (int r = 0; r < 3; ++r) need(T.angles[3 * k + r]);
         for (int k : tt) for (int r = 0; r < 4; ++r) need(T.torsions[4 * k + r]);
         uniq(halo);
-        if (n_own + (int)halo.size() >= 0x7fff) return 1;
+        const int n_at = n_own + (int)halo.size();
+        if (3 * n_at > PF * BT || n_at >= 0x7fff) return 1;
         auto local = [&](int a) -> uint32_t {
             if (a >= a0 && a < a0 + n_own) return (uint32_t)(a - a0);
             return (uint32_t)(n_own + (std::lower_bound(halo.begin(), halo.end(), a) - halo.begin()));
         };
-        // slots: contiguous per own atom, in the order (bonds, angles, torsions) x role
-        std::vector<std::vector<std::array<int, 3>>> per_atom(n_own);  // (type, pos in tile list, role)
-        for (size_t q = 0; q < tb.size(); ++q) for (int r = 0; r < 2; ++r) { int a = T.bonds[2 * tb[q] + r]; if (a >= a0 && a < a0 + n_own) per_atom[a - a0].push_back({0, (int)q, r}); }
-        for (size_t q = 0; q < ta.size(); ++q) for (int r = 0; r < 3; ++r) { int a = T.angles[3 * ta[q] + r]; if (a >= a0 && a < a0 + n_own) per_atom[a - a0].push_back({1, (int)q, r}); }
-        for (size_t q = 0; q < tt.size(); ++q) for (int r = 0; r < 4; ++r) { int a = T.torsions[4 * tt[q] + r]; if (a >= a0 && a < a0 + n_own) per_atom[a - a0].push_back({2, (int)q, r}); }
-        std::vector<std::array<uint32_t, 2>> sb(tb.size());
-        std::vector<std::array<uint32_t, 3>> sa(ta.size());
-        std::vector<std::array<uint32_t, 4>> st(tt.size());
-        int n_slots = 0;
-        for (auto& v : per_atom) n_slots += (int)v.size();
-        if (n_slots >= 0xffff) return 1;
-        const uint32_t dump = (uint32_t)n_slots;
-        for (auto& s : sb) s.fill(dump);
-        for (auto& s : sa) s.fill(dump);
-        for (auto& s : st) s.fill(dump);
-        bt.csr_off = (int)csr_all.size();
-        int slot = 0;
+        // slot of (own atom la, its k-th incident role) = k*stride + la; roles on halo atoms go to the dump slot
+        std::map<std::array<int, 3>, uint32_t> slot_of;
+        bt.cnt_off = (int)cnt_all.size();
         for (int la = 0; la < n_own; ++la) {
-            csr_all.push_back(slot);
-            for (auto& e : per_atom[la]) {
-                if (e[0] == 0) sb[e[1]][e[2]] = slot; else if (e[0] == 1) sa[e[1]][e[2]] = slot; else st[e[1]][e[2]] = slot;
-                ++slot;
-            }
+            const auto& v = inc[a0 + la];
+            for (size_t k = 0; k < v.size(); ++k) slot_of[{v[k].type, v[k].idx, v[k].role}] = (uint32_t)(k * stride + la);
+            cnt_all.push_back((int)v.size());
         }
-        csr_all.push_back(slot);
-        bt.n_slots = n_slots;
+        auto slot = [&](int type, int idx, int role) -> uint32_t {
+            auto it = slot_of.find({type, idx, role});
+            return it == slot_of.end() ? dump : it->second;
+        };
         auto owner = [&](int first_atom) { return (first_atom >= a0 && first_atom < a0 + n_own) ? OWNER : 0u; };
-        bt.bond_off = (int)bonds_all.size(); bt.n_bond = (int)tb.size();
-        for (size_t q = 0; q < tb.size(); ++q) {
-            const int k = tb[q];
+        const uint32_t l1 = std::min(1, n_at - 1), l2 = std::min(2, n_at - 1), l3 = std::min(3, n_at - 1);
+
+        bt.bond_off = (int)bonds_all.size();
+        for (int k : tb) {
             BondRec r{};
             r.ij = local(T.bonds[2 * k]) | owner(T.bonds[2 * k]) | (local(T.bonds[2 * k + 1]) << 16);
-            r.slots = sb[q][0] | (sb[q][1] << 16);
+            r.slots = slot(0, k, 0) | (slot(0, k, 1) << 16);
             r.r0 = (float)T.bond_para[2 * k]; r.k = (float)T.bond_para[2 * k + 1];
             bonds_all.push_back(r);
         }
-        bt.angle_off = (int)angles_all.size(); bt.n_angle = (int)ta.size();
-        for (size_t q = 0; q < ta.size(); ++q) {
-            const int k = ta[q];
+        while ((bonds_all.size() - bt.bond_off) % 32) bonds_all.push_back(BondRec{0u | (l1 << 16), dump | (dump << 16), 0.f, 0.f});
+        bt.n_bond = (int)bonds_all.size() - bt.bond_off;
+
+        bt.angle_off = (int)angles_all.size();
+        for (int k : ta) {
             AngleRec r{};
             r.ij = local(T.angles[3 * k]) | owner(T.angles[3 * k]) | (local(T.angles[3 * k + 1]) << 16);
             r.k = local(T.angles[3 * k + 2]);
-            r.s_ij = sa[q][0] | (sa[q][1] << 16); r.s_k = sa[q][2];
+            r.s_ij = slot(1, k, 0) | (slot(1, k, 1) << 16); r.s_k = slot(1, k, 2);
             r.th0 = (float)T.angle_para[2 * k]; r.kf = (float)T.angle_para[2 * k + 1];
             angles_all.push_back(r);
         }
-        bt.tors_off = (int)tors_all.size(); bt.n_tors = (int)tt.size();
-        for (size_t q = 0; q < tt.size(); ++q) {
-            const int k = tt[q];
+        while ((angles_all.size() - bt.angle_off) % 32) {
+            AngleRec r{};
+            r.ij = 0u | (l1 << 16); r.k = l2; r.s_ij = dump | (dump << 16); r.s_k = dump;
+            angles_all.push_back(r);
+        }
+        bt.n_angle = (int)angles_all.size() - bt.angle_off;
+
+        bt.tors_off = (int)tors_all.size();
+        for (int k : tt) {
             TorsRec r{};
             r.ij = local(T.torsions[4 * k]) | owner(T.torsions[4 * k]) | (local(T.torsions[4 * k + 1]) << 16);
             r.kl = local(T.torsions[4 * k + 2]) | (local(T.torsions[4 * k + 3]) << 16);
-            r.s_ij = st[q][0] | (st[q][1] << 16); r.s_kl = st[q][2] | (st[q][3] << 16);
+            r.s_ij = slot(2, k, 0) | (slot(2, k, 1) << 16); r.s_kl = slot(2, k, 2) | (slot(2, k, 3) << 16);
             r.c0 = t_coef[k][0];
             for (int n = 0; n < NF; ++n) { r.cg[n] = t_coef[k][1 + n]; r.sg[n] = t_coef[k][1 + NF + n]; }
             tors_all.push_back(r);
         }
+        while ((tors_all.size() - bt.tors_off) % 32) {
+            TorsRec r{};
+            r.ij = 0u | (l1 << 16); r.kl = l2 | (l3 << 16); r.s_ij = dump | (dump << 16); r.s_kl = dump | (dump << 16);
+            tors_all.push_back(r);
+        }
+        bt.n_tors = (int)tors_all.size() - bt.tors_off;
+
         bt.halo_off = (int)halo_all.size(); bt.n_halo = (int)halo.size();
         halo_all.insert(halo_all.end(), halo.begin(), halo.end());
-        max_slots = std::max(max_slots, n_slots + 1);
-        max_atoms = std::max(max_atoms, n_own + (int)halo.size());
+        max_atoms = std::max(max_atoms, n_at);
         tiles.push_back(bt);
     }
-    E->n_tiles = (int)tiles.size(); E->max_slots = max_slots; E->max_atoms = max_atoms;
-    E->bonded_smem = (size_t)(max_slots + max_atoms) * sizeof(float4);
+    const size_t smem = ((size_t)max_atoms + (size_t)max_cnt * stride + 1) * sizeof(float4);
+    if (smem > BONDED_SMEM_CAP && tile_atoms > 32) return 1;
+    E->n_tiles = (int)tiles.size(); E->tile_atoms = tile_atoms; E->slot_stride = stride; E->max_cnt = max_cnt;
+    E->max_atoms = max_atoms; E->bonded_smem = smem;
     int rc;
     if ((rc = upload(E, &E->d_tiles, tiles))) return rc;
     if ((rc = upload(E, &E->d_halo, halo_all))) return rc;
     if ((rc = upload(E, &E->d_bonds, bonds_all))) return rc;
     if ((rc = upload(E, &E->d_angles, angles_all))) return rc;
     if ((rc = upload(E, &E->d_tors, tors_all))) return rc;
-    if ((rc = upload(E, &E->d_csr, csr_all))) return rc;
+    if ((rc = upload(E, &E->d_cnt, cnt_all))) return rc;
     return MLP_OK;
 }
 
@@ -827,6 +884,7 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     for (auto& kv : ex) {
         const int I = kv.first.first, J = kv.first.second;
         pairs.push_back(make_int2(I, J));
+        // uint16 [g][lane]: bit 4a+b <-> pair (i = lane+32a, j = 4g+b) allowed
         std::vector<uint16_t> m16((size_t)32 * 32, 0xffffu);
         auto clear = [&](int li, int lj) { m16[(size_t)(lj >> 2) * 32 + (li & 31)] &= (uint16_t)~(1u << (4 * (li >> 5) + (lj & 3))); };
         if (I == J)
@@ -842,14 +900,41 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
         for (int J = I; J < nt; ++J)
             if (!ex.count({I, J})) pairs.push_back(make_int2(I, J));
     E->n_pairs = (int)pairs.size();
+    // per tile: the partial-force blocks to sum (pair index order, i-side before j-side)
+    std::vector<std::vector<int>> lists(nt);
+    for (int p = 0; p < E->n_pairs; ++p) {
+        lists[pairs[p].x].push_back(2 * p);
+        lists[pairs[p].y].push_back(2 * p + 1);
+    }
+    std::vector<int> red_off(nt + 1, 0), red_list;
+    for (int t = 0; t < nt; ++t) {
+        red_list.insert(red_list.end(), lists[t].begin(), lists[t].end());
+        red_off[t + 1] = (int)red_list.size();
+    }
     int rc;
     if ((rc = upload(E, &E->d_pairs, pairs))) return rc;
     if ((rc = upload(E, &E->d_masks, masks))) return rc;
     if ((rc = upload(E, &E->d_q, q))) return rc;
     if ((rc = upload(E, &E->d_par, par))) return rc;
-    std::vector<float> ones(4, 1.f);
-    if ((rc = upload(E, &E->d_ones, ones))) return rc;
+    if ((rc = upload(E, &E->d_red_off, red_off))) return rc;
+    if ((rc = upload(E, &E->d_red_list, red_list))) return rc;
     return MLP_OK;
+}
+
+struct Workspace { size_t e_bonded, e_nb, xq, fpart, total; };
+
+Workspace layout(const mlp_energy* e, int64_t B, uint32_t term_mask, bool grad) {
+    Workspace w{};
+    size_t off = 0;
+    w.e_bonded = off; off += align256((size_t)B * std::max(e->n_tiles, 1) * 3 * sizeof(float));
+    w.e_nb = off;
+    if (term_mask & MLP_TERM_NB) off += align256((size_t)B * e->n_pairs * sizeof(double));
+    w.xq = off;
+    if (term_mask & MLP_TERM_NB) off += align256((size_t)B * e->Npad * sizeof(float4));
+    w.fpart = off;
+    if ((term_mask & MLP_TERM_NB) && grad) off += align256((size_t)B * e->n_pairs * 6 * NB_T * sizeof(float));
+    w.total = off + 256;
+    return w;
 }
 
 }  // namespace
@@ -880,10 +965,10 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
     cudaDeviceGetAttribute(&E->sm_count, cudaDevAttrMultiProcessorCount, device);
     int rc = MLP_OK;
     int tile = BT;
-    if (const char* env = std::getenv("MLP_BONDED_TILE")) tile = std::max(32, std::min(BT, std::atoi(env)));
+    if (const char* env = std::getenv("MLP_BONDED_TILE")) tile = std::max(32, std::min(BT, std::atoi(env) & ~31));
     while (true) {
         rc = pack_bonded(E, *t, tile);
-        if (rc == 1 && tile > 32) { tile /= 2; for (void* p : E->allocs) cudaFree(p); E->allocs.clear(); continue; }
+        if (rc == 1 && tile > 32) { tile -= 32; for (void* p : E->allocs) cudaFree(p); E->allocs.clear(); continue; }
         break;
     }
     if (rc == 1) { mlp_set_error("mlp_energy_create: topology too dense for the bonded tile"); rc = MLP_E_ARG; }
@@ -904,14 +989,23 @@ void mlp_energy_destroy(mlp_energy* e) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(e->device);
+    for (int k = 0; k < 4; ++k)
+        for (auto& p : e->pending[k]) { cudaEventDestroy(p[0]); cudaEventDestroy(p[1]); }
     for (void* p : e->allocs) cudaFree(p);
     cudaSetDevice(prev);
     delete e;
 }
 
-int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B) {
+int mlp_energy_info(const mlp_energy* e, int64_t info[8]) {
+    if (!e || !info) { mlp_set_error("mlp_energy_info: null argument"); return MLP_E_ARG; }
+    info[0] = e->n_tiles; info[1] = e->tile_atoms; info[2] = e->max_cnt; info[3] = (int64_t)e->bonded_smem;
+    info[4] = e->n_nbt; info[5] = e->n_pairs; info[6] = e->n_masked; info[7] = e->Npad;
+    return MLP_OK;
+}
+
+int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B, uint32_t term_mask, int want_grad) {
     if (!e || B < 0) return MLP_E_ARG;
-    return 256 + B * 4 * (int64_t)sizeof(double) + 256 + B * (int64_t)e->Npad * (int64_t)sizeof(float4);
+    return (int64_t)layout(e, B, term_mask, want_grad != 0).total;
 }
 
 int mlp_energy_last_launches(const mlp_energy* e) { return e ? e->last_launches : 0; }
@@ -946,23 +1040,23 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     if (!e || B < 0 || (term_mask & ~MLP_TERM_ALL)) { mlp_set_error("mlp_energy_eval: bad argument"); return MLP_E_ARG; }
     if (B == 0 || e->N == 0) { e->last_launches = 0; return MLP_OK; }  // empty batch: nothing to do (pointers may be null)
     if (!x || !workspace) { mlp_set_error("mlp_energy_eval: null x / workspace"); return MLP_E_ARG; }
-    if (workspace_bytes < mlp_energy_workspace_bytes(e, B)) { mlp_set_error("mlp_energy_eval: workspace too small"); return MLP_E_WORKSPACE; }
+    const Workspace W = layout(e, B, term_mask, grad != nullptr);
+    if (workspace_bytes < (int64_t)W.total) { mlp_set_error("mlp_energy_eval: workspace too small"); return MLP_E_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(workspace) & 15) { mlp_set_error("mlp_energy_eval: workspace must be 16-byte aligned"); return MLP_E_ARG; }
-    e->last_launches = 0;
-    if (B == 0 || e->N == 0) return MLP_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     int prev = 0;
     CK(cudaGetDevice(&prev));
     if (prev != e->device) CK(cudaSetDevice(e->device));
     char* ws = static_cast<char*>(workspace);
-    double* acc = reinterpret_cast<double*>(ws);
-    size_t off = ((size_t)B * 4 * sizeof(double) + 255) & ~(size_t)255;
-    float4* xq = reinterpret_cast<float4*>(ws + off);
+    ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
+    float* e_bonded = reinterpret_cast<float*>(ws + W.e_bonded);
+    double* e_nb = reinterpret_cast<double*>(ws + W.e_nb);
+    float4* xq = reinterpret_cast<float4*>(ws + W.xq);
+    float* fpart = reinterpret_cast<float*>(ws + W.fpart);
     const int N = e->N;
     const bool accumulate = flags & MLP_EVAL_ACCUMULATE_GRAD;
+    const bool bonded = term_mask & MLP_TERM_BONDED, nonbonded = term_mask & MLP_TERM_NB;
     int launches = 0;
-    if (energies) { CK(cudaMemsetAsync(acc, 0, (size_t)B * 4 * sizeof(double), stream)); ++launches; }
-    double* acc_arg = energies ? acc : nullptr;
 
     auto prof_begin = [&](int k) {
         if (!e->profile) return;
@@ -973,24 +1067,26 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     };
     auto prof_end = [&](int k) { if (e->profile) cudaEventRecord(e->pending[k].back()[1], stream); };
 
-    if (term_mask & MLP_TERM_BONDED) {
+    if (bonded) {
         prof_begin(1);
         int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
         dim3 grid(e->n_tiles, (unsigned)((B + cpc - 1) / cpc));
         if (grad)
-            bonded_kernel<true><<<grid, BT, e->bonded_smem, stream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_csr,
-                x, sxb, sxc, sxn, grad, sgb, sgc, sgn, weights, acc_arg, (int)B, cpc, term_mask & MLP_TERM_BONDED, accumulate, e->max_atoms);
+            bonded_kernel<true><<<grid, BT, e->bonded_smem, stream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
+                x, sxb, sxc, sxn, grad, sgb, sgc, sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc,
+                term_mask & MLP_TERM_BONDED, accumulate, e->max_atoms, e->slot_stride, e->max_cnt);
         else
-            bonded_kernel<false><<<grid, BT, e->bonded_smem, stream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_csr,
-                x, sxb, sxc, sxn, nullptr, 0, 0, 0, weights, acc_arg, (int)B, cpc, term_mask & MLP_TERM_BONDED, 0, e->max_atoms);
+            bonded_kernel<false><<<grid, BT, e->bonded_smem, stream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
+                x, sxb, sxc, sxn, nullptr, 0, 0, 0, weights, energies ? e_bonded : nullptr, (int)B, cpc,
+                term_mask & MLP_TERM_BONDED, 0, e->max_atoms, e->slot_stride, e->max_cnt);
         prof_end(1);
         ++launches;
-    } else if (grad && !accumulate) {
+    } else if (grad && !accumulate && !nonbonded) {
         long n = (long)B * N * 3;
         zero_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad, sgb, sgc, sgn, N, (int)B);
         ++launches;
     }
-    if (term_mask & MLP_TERM_NB) {
+    if (nonbonded) {
         long n = (long)B * e->Npad;
         prof_begin(0);
         nb_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, xq, N, e->Npad, (int)B);
@@ -1000,16 +1096,23 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         long items = (long)B * e->n_pairs;
         unsigned blocks = (unsigned)((items + NB_WARPS - 1) / NB_WARPS);
         const bool full = e->nb_mode == MLP_NB_FULL;
-#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(xq, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, e->n_masked, e->Npad, N, (int)B, grad, sgb, sgc, sgn, weights, acc_arg)
+        double* ep = energies ? e_nb : nullptr;
+#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(xq, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, e->n_masked, e->Npad, (int)B, fpart, weights, ep)
         if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
         else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
 #undef NB_LAUNCH
         prof_end(2);
         ++launches;
+        if (grad) {
+            prof_begin(3);
+            nb_reduce_kernel<<<dim3(e->n_nbt, (unsigned)B), NB_T, 0, stream>>>(fpart, e->d_red_off, e->d_red_list, e->n_pairs, N,
+                grad, sgb, sgc, sgn, weights, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0);
+            prof_end(3);
+            ++launches;
+        }
     }
     if (energies) {
-        int n = (int)(B * 4);
-        finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(acc, energies, n);
+        finalize_kernel<<<(unsigned)B, 128, 0, stream>>>(e_bonded, e->n_tiles, e_nb, e->n_pairs, energies, term_mask);
         ++launches;
     }
     e->last_launches = launches;
@@ -1021,8 +1124,8 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
 
 int mlp_rmsd_eval(const float* x, int64_t B, int64_t N, int64_t sxb, int64_t sxc, int64_t sxn, float scale, float shift,
                   const float* targets, int64_t K, float* out, void* stream_) {
-    if (!x || !targets || !out || B < 0 || N <= 0 || K <= 0 || K > 65535) { mlp_set_error("mlp_rmsd_eval: bad argument"); return MLP_E_ARG; }
     if (B == 0) return MLP_OK;
+    if (!x || !targets || !out || B < 0 || N <= 0 || K <= 0 || K > 65535) { mlp_set_error("mlp_rmsd_eval: bad argument"); return MLP_E_ARG; }
     rmsd_kernel<<<dim3((unsigned)B, (unsigned)K), 256, 0, static_cast<cudaStream_t>(stream_)>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, out);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { mlp_set_error(std::string("rmsd kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }

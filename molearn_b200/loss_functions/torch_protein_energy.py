@@ -38,7 +38,7 @@ class _DeviceEnergy:
         """x: [B,3,N] logical fp32 CUDA tensor (any strides). energies [B,4] or None; grad like x or None."""
         L = _lib.lib()
         B = x.shape[0]
-        nbytes = L.mlp_energy_workspace_bytes(self._h, B)
+        nbytes = L.mlp_energy_workspace_bytes(self._h, B, term_mask, int(grad is not None))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         gs = (grad.stride(0), grad.stride(1), grad.stride(2)) if grad is not None else (0, 0, 0)
         stream = torch.cuda.current_stream(x.device).cuda_stream
@@ -60,7 +60,15 @@ class _DeviceEnergy:
         ms, n = np.zeros(4, np.float64), np.zeros(4, np.int64)
         _lib.check(_lib.lib().mlp_energy_profile_read(self._h, ms.ctypes.data_as(ctypes.c_void_p),
                                                       n.ctypes.data_as(ctypes.c_void_p)))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("nb_pack", "bonded", "nb"))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("nb_pack", "bonded", "nb", "nb_reduce"))}
+
+    def info(self):
+        import numpy as np
+        v = np.zeros(8, np.int64)
+        _lib.check(_lib.lib().mlp_energy_info(self._h, v.ctypes.data_as(ctypes.c_void_p)))
+        keys = ("bonded_tiles", "bonded_tile_atoms", "max_contributions_per_atom", "bonded_smem_bytes",
+                "nb_tiles", "nb_tile_pairs", "nb_masked_tile_pairs", "n_atoms_padded")
+        return dict(zip(keys, (int(a) for a in v)))
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -209,8 +209,8 @@ def test_large_batch_properties(dev, energy_objs, golden_energy):
     x = xb.permute(0, 2, 1).requires_grad_(True)
     e = tpe.energy_per_conformation(x)
     e.sum().backward()
-    net = x.grad.sum(dim=2)                                           # [B,3] net force
-    assert float(net.abs().max()) < 2e-2
+    net = x.grad.double().sum(dim=2)                                  # [B,3] net force: zero up to fp32 rounding
+    assert float((net.abs() / x.grad.double().abs().sum(dim=2)).max()) < 1e-6
     q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g).double())
     moved = ((xb.double() - xb.double().mean(1, keepdim=True)) @ q.to(dev)).float().contiguous()
     e2 = tpe.energy_per_conformation(moved.permute(0, 2, 1))

@@ -26,7 +26,12 @@ def analysis(murd_data):
     from molearn_b200.models import AutoEncoder
     torch.manual_seed(0)
     net = AutoEncoder(out_points=murd_data.dataset.shape[1]).to("cuda:0")
-    ma = MolearnAnalysis(batch_size=16)
+    # one decode batch = the whole 6x6 grid, and no TF32: decoding the same points in a different
+    # batch (or with a different cuDNN algorithm) moves the random-init network's collapsed,
+    # ill-conditioned structures by more than the energy tolerance
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ma = MolearnAnalysis(batch_size=36)
     ma.set_network(net)
     ma.set_dataset("train", murd_data)
     ma.setup_grid(samples=6, padding=0.1)
