@@ -171,6 +171,98 @@ def workload_config(n_atoms):
 
 
 # ---------------------------------------------------------------------------------------------
+def run_scan(dev, rank, world, info, frames, G, barrier):
+    """MurD latent-grid scan GxG: decode (FoldingNet, cuDNN) + 4 energy terms + RMSD to the 16 dataset
+    frames per point, through MolearnAnalysis.scan_scores; grid points sharded over the ranks and
+    gathered with one all_gather.  points/s = G^2 / max-over-ranks time (strong scaling)."""
+    import torch.distributed as dist
+    from molearn_b200.analysis import MolearnAnalysis
+    from molearn_b200.data import CoordinateSet
+    from molearn_b200.models import AutoEncoder
+    data = CoordinateSet(info, frames).prepare_dataset()
+    torch.manual_seed(0)
+    net = AutoEncoder(out_points=frames.shape[1]).to(dev)
+    ma = MolearnAnalysis(batch_size=256)
+    ma.set_network(net)
+    ma.set_dataset("murd", data)
+    targets = torch.from_numpy(frames)
+    ma.setup_grid(samples=32, padding=0.1)
+    ma.scan_scores(targets=targets)                                     # warm-up: cuDNN algorithm choice, allocator
+    ma.setup_grid(samples=G, padding=0.1)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rows = ma.scan_scores(targets=targets)                              # ends with the gather + D2H of [G^2, 20]
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    # share of the energy + RMSD kernels: the same batches without the decoder
+    tpe = ma.physics()
+    xb = torch.randn(256, frames.shape[1], 3, device=dev) * 5 + torch.from_numpy(frames[0]).to(dev)
+    tg = targets.to(dev)
+    from molearn_b200.analysis import rmsd_to_targets
+    n_batches = -(-ma.scan_stats["points_this_rank"] // 256)
+    for _ in range(2):
+        tpe.energy_per_conformation(xb.permute(0, 2, 1))
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(n_batches):
+        tpe.energy_per_conformation(xb.permute(0, 2, 1))
+        rmsd_to_targets(xb, tg)
+    s1.record()
+    torch.cuda.synchronize()
+    score_ms = s0.elapsed_time(s1)
+    return {"metric": "latent-grid points/sec (MurD, decode + 4 energy terms + RMSD to 16 frames)", "grid": G,
+            "value": G * G / (ms * 1e-3), "unit": "points/s", "ms": ms, "scaling": "strong", "n_gpus": world,
+            "columns": int(rows.shape[1]), "gather_bytes": ma.scan_stats["gather_bytes"],
+            "points_this_rank": ma.scan_stats["points_this_rank"],
+            "energy_rmsd_kernels_ms_this_rank": score_ms, "energy_rmsd_share": score_ms / ms,
+            "decoder": "FoldingNet AutoEncoder(out_points=2145), random init seed 0, torch default conv math (cuDNN)",
+            "wall_s": time.perf_counter() - t0}
+
+
+def run_config4(dev, info, frames, pk):
+    """BASELINE config 4: synthetic 10 715-atom system (5 MurD tiles), all four terms + gradient, B = 128."""
+    from molearn_b200 import TorchProteinEnergy, _lib
+    from molearn_b200.data import tile_system
+    BB = 128
+    tinfo, x = tile_system(info, frames, 5, batch=BB, noise=0.05, seed=1234)
+    tpe = TorchProteinEnergy(None, tinfo, device=dev)
+    dv = tpe._dev()
+    xd = torch.from_numpy(x).to(dev)
+    g = torch.empty_like(xd)
+    e = torch.empty((BB, 4), device=dev)
+    for _ in range(2):
+        dv.eval(xd.permute(0, 2, 1), e, g.permute(0, 2, 1), None, _lib.TERM_ALL)
+    torch.cuda.synchronize()
+    dv.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    K = 5
+    for _ in range(K):
+        dv.eval(xd.permute(0, 2, 1), e, g.permute(0, 2, 1), None, _lib.TERM_ALL)
+    e1.record()
+    torch.cuda.synchronize()
+    pr = dv.profile_read()
+    dv.profile(False)
+    ms = e0.elapsed_time(e1) / K
+    nb_ms = pr["nb"][0] / pr["nb"][1]
+    flops = FLOPS_PER_PAIR * tpe.topology.n_nb_pairs * BB
+    peak = 148 * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    return {"n_atoms": tpe.n_atoms, "batch": BB, "conformations_per_s": BB / (ms * 1e-3), "ms_per_step": ms,
+            "pairs_per_s": tpe.topology.n_nb_pairs * BB / (nb_ms * 1e-3), "nb_kernel_ms": nb_ms,
+            "nb_fp32_frac": flops / (nb_ms * 1e-3) / 1e12 / peak, "bonded_kernel_ms": pr["bonded"][0] / pr["bonded"][1],
+            "nb_reduce_ms": pr["nb_reduce"][0] / pr["nb_reduce"][1], "info": dv.info(),
+            "note": "input (16.5 MB) < L2; the NB kernel is FMA-bound, its traffic is the 1.4 GB partial-force scratch"}
+
+
+# ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,7 +270,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip roofline_bonded / large-N extras")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline_bonded / scan / large-N extras")
+    ap.add_argument("--scan-grid", type=int, default=256, help="G of the GxG latent grid of the scan section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -238,12 +331,12 @@ def main():
             ms = float(t)
         return ms
 
+    l0 = dv.launches
+    step(0)
+    launches = (dv.launches - l0) * args.steps          # kernels of ours launched inside the timed region
     clocks = ClockSampler(local)
     clocks.start()
-    l0 = dv.launches
     ms = timed(step, args.steps, args.warmup)
-    launches = dv.launches - l0 - 0
-    launches = launches * args.steps // (args.steps + args.warmup)
     clk = clocks.stop()
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -273,6 +366,10 @@ def main():
         "dtype": "f32", "data": "synthetic", "config": workload_config(N), "clocks": clk, "e2e": e2e,
         "gpu_launches": int(launches),
     }
+
+    # ---- latent-grid scan (BASELINE config 3): sharded over the ranks, one all-gather --------------
+    if not args.no_extras:
+        out["scan"] = run_scan(dev, rank, world, info, frames, args.scan_grid, barrier)
 
     if rank == 0:
         # ---- per-kernel durations (CUDA events on the launching stream, inside the C ABI) ----
@@ -315,6 +412,8 @@ def main():
                                       "traffic": None, "algorithmic_bytes_per_launch": byts, "kernel_ms": t_ms,
                                       "conformations_per_s": BB / (t_ms * 1e-3)}
             del xb, gb, eb
+        if world == 1 and not args.no_extras:
+            out["config4_10k_atoms"] = run_config4(dev, info, frames, pk)
         if world == 1 and not args.no_cpu_baseline:
             rate, sec, cores = cpu_port_rate(top.as_dict(), make_batch(frames, 0)[:CPU_SAMPLE], reps=5)
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

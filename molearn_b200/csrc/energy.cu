@@ -54,6 +54,9 @@ constexpr int NB_WARPS = 4;      // warps per CTA, one work item each
 #ifndef NB_MINB
 #define NB_MINB 4
 #endif
+#ifndef NB_UNROLL
+#define NB_UNROLL 1
+#endif
 constexpr float LJ_K = 1.9f, C_K = 0.4f;  // warp thresholds, torch_protein_energy.py:233-234
 constexpr float CLAMP = 0.999999f;        // acos clamp, :289
 constexpr size_t BONDED_SMEM_CAP = 100 * 1024;  // keep two CTAs per SM
@@ -565,7 +568,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     const int src_lane = (lane + 1) & 31;
     const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m[warp]);
 
-#pragma unroll 1
+#pragma unroll NB_UNROLL
     for (int r = 0; r < 32; ++r) {
         const int g = (lane + r) & 31;
         float4 xj[4];
