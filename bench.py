@@ -181,6 +181,7 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
     from molearn_b200.models import AutoEncoder
     data = CoordinateSet(info, frames).prepare_dataset()
     torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True                               # fixed decode batch shape: let cuDNN pick its best algorithm
     net = AutoEncoder(out_points=frames.shape[1]).to(dev)
     ma = MolearnAnalysis(batch_size=256)
     ma.set_network(net)
