@@ -162,15 +162,18 @@ int mlp_energy_profile(mlp_energy* e, int enable);
 int mlp_energy_profile_read(mlp_energy* e, double ms[4], int64_t counts[4]);
 
 /* Per-conformation RMSD to K target structures (scan reducers; replaces the NumPy / biobox
- * loops of MolearnAnalysis.scan_error_from_target / scan_error, analyser.py:626-737, with the
- * intended per-point formula sqrt(mean_atoms sum_xyz d^2), SURVEY S-3/S-4).
+ * loops of MolearnAnalysis.scan_error_from_target / scan_error / get_error, analyser.py:277-305,
+ * 626-737, with the intended per-point formula sqrt(mean_atoms sum_xyz d^2), SURVEY S-3/S-4).
  *   x        dev [B,3,N] logical with strides as above;  value used is x*scale + shift
  *   targets  dev [K,N,3] fp32 contiguous (Angstrom)
  *   out      dev [B,K] fp32
+ *   flags    MLP_RMSD_ALIGN: RMSD after optimal rigid superposition (Kabsch / Horn quaternion
+ *            eigenvalue, fp64) - what biobox Molecule.rmsd computes at analyser.py:297, 671
  */
+#define MLP_RMSD_ALIGN 1u
 int mlp_rmsd_eval(const float* x, int64_t B, int64_t N,
                   int64_t sxb, int64_t sxc, int64_t sxn, float scale, float shift,
-                  const float* targets, int64_t K, float* out, void* stream);
+                  const float* targets, int64_t K, float* out, uint32_t flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ SYMBOLS = {
     "mlp_energy_profile": (c_int, [c_void_p, c_int]),
     "mlp_energy_profile_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mlp_rmsd_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_float,
-                              c_void_p, c_int64, c_void_p, c_void_p]),
+                              c_void_p, c_int64, c_void_p, c_uint32, c_void_p]),
 }
 
 E_ARG, E_IO, E_KEY, E_PARSE, E_CUDA, E_NOGPU, E_WORKSPACE = -1, -2, -3, -4, -5, -6, -7
@@ -43,6 +43,7 @@ TERM_BOND, TERM_ANGLE, TERM_TORSION, TERM_NB, TERM_BONDED, TERM_ALL = 1, 2, 4, 8
 NB_REPULSIVE, NB_FULL = 0, 1
 TOPO_FIX_H = 1
 EVAL_ACCUMULATE_GRAD = 1
+RMSD_ALIGN = 1
 
 
 def library_path() -> str:

@@ -155,6 +155,20 @@ class MolearnAnalysis:
     def set_decoded(self, key, structures):
         self._decoded[key] = structures
 
+    def get_error(self, key, align=True):
+        """RMSD (Angstrom) between every structure of a dataset and its encode->decode reconstruction
+        (analyser.py:277-305); 1-D NumPy array.  ``align=True``: after optimal superposition."""
+        ds = self.get_dataset(key)
+        out = []
+        with torch.no_grad():
+            for slc in self._slices(ds.shape[0]):
+                xb = ds[slc].to(self.device)
+                dec = self.network.decode(self.network.encode(xb))[:, :self.n_atoms, :]
+                tgt = (xb * self.stdval + self.meanval).contiguous()
+                full = rmsd_to_targets(dec, tgt, self.stdval, self.meanval, align=align)    # [b, b]; the diagonal pairs i with i
+                out.append(full.diagonal().cpu())
+        return torch.cat(out).numpy()
+
     def num_trainable_params(self):
         return sum(p.numel() for p in self.network.parameters() if p.requires_grad)
 
@@ -241,9 +255,9 @@ class MolearnAnalysis:
             self.surfaces[key] = self._surface(rows.sum(dim=1))
         return self.surfaces[key], self.xvals, self.yvals
 
-    def scan_error_from_target(self, key, index=None, align=False):
-        """RMSD surface against one target structure (analyser.py:626-683).  ``align=False``:
-        unaligned RMSD in Angstrom between ``decoded*std+mean`` and the target."""
+    def scan_error_from_target(self, key, index=None, align=True):
+        """RMSD surface (Angstrom) between ``decoded*std+mean`` and one target structure
+        (analyser.py:626-683).  ``align=True`` (the reference default): after optimal superposition."""
         s_key = f"RMSD_from_{key}" if index is None else f"RMSD_from_{key}_index_{index}"
         if s_key not in self.surfaces:
             if "grid" not in self._encoded:
@@ -252,10 +266,8 @@ class MolearnAnalysis:
             if target.shape[0] != 1:
                 raise Exception(f"dataset {key} shape is {target.shape}. A dataset with a single conformation is expected. "
                                 "Either pass a key that points to a single structure or pass the index of the structure you want")
-            if align:
-                raise NotImplementedError("aligned (Kabsch) RMSD is not on the device path yet; pass align=False")
             tgt = target.to(self.device)
-            rows = self._scan_rows(1, lambda z, dec: rmsd_to_targets(dec, tgt, self.stdval, self.meanval))
+            rows = self._scan_rows(1, lambda z, dec: rmsd_to_targets(dec, tgt, self.stdval, self.meanval, align=align))
             self.surfaces[s_key] = self._surface(rows[:, 0])
         return self.surfaces[s_key], self.xvals, self.yvals
 

@@ -11,9 +11,10 @@ import torch
 from .. import _lib
 
 
-def rmsd_to_targets(x, targets, scale: float = 1.0, shift: float = 0.0):
-    """Unaligned RMSD ``sqrt(mean_atoms sum_xyz (x*scale+shift - t)^2)`` of every structure to
-    every target (the intended per-point formula, SURVEY S-3/S-4).
+def rmsd_to_targets(x, targets, scale: float = 1.0, shift: float = 0.0, align: bool = False):
+    """RMSD ``sqrt(mean_atoms sum_xyz (x*scale+shift - t)^2)`` of every structure to every target
+    (the intended per-point formula, SURVEY S-3/S-4).  ``align=True``: after optimal rigid
+    superposition (Kabsch), the quantity biobox ``Molecule.rmsd`` returns in the reference.
 
     :param x: ``[B, N, 3]`` float32 CUDA tensor (any strides - e.g. a slice of a decoder output).
     :param targets: ``[K, N, 3]`` float32 CUDA tensor, in the units of ``x*scale+shift``.
@@ -31,5 +32,6 @@ def rmsd_to_targets(x, targets, scale: float = 1.0, shift: float = 0.0):
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().mlp_rmsd_eval(x.data_ptr(), B, N, x.stride(0), x.stride(2), x.stride(1),
                                             float(scale), float(shift), targets.data_ptr(), K, out.data_ptr(),
+                                            _lib.RMSD_ALIGN if align else 0,
                                             torch.cuda.current_stream(x.device).cuda_stream))
     return out

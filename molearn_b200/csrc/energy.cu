@@ -568,7 +568,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     const int src_lane = (lane + 1) & 31;
     const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m[warp]);
 
-#pragma unroll NB_UNROLL
+#pragma unroll 1
     for (int r = 0; r < 32; ++r) {
         const int g = (lane + r) & 31;
         float4 xj[4];
@@ -692,6 +692,86 @@ rmsd_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, float sca
         float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
         v = warp_sum(v);
         if (threadIdx.x == 0) out[(long)b * K + k] = sqrtf(v / (float)N);
+    }
+}
+
+// Largest eigenvalue of a symmetric 4x4 matrix by cyclic Jacobi rotations (fp64, one thread).
+__device__ double max_eig_sym4(double a[4][4]) {
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 4; ++p) for (int q = p + 1; q < 4; ++q) off += a[p][q] * a[p][q];
+        if (off < 1e-28 * (a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2] + a[3][3] * a[3][3]) || off == 0.0) break;
+        for (int p = 0; p < 4; ++p)
+            for (int q = p + 1; q < 4; ++q) {
+                if (a[p][q] == 0.0) continue;
+                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 4; ++k) {  // A <- A J
+                    double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - s * akq; a[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 4; ++k) {  // A <- J^T A
+                    double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - s * aqk; a[q][k] = s * apk + c * aqk;
+                }
+            }
+    }
+    return fmax(fmax(a[0][0], a[1][1]), fmax(a[2][2], a[3][3]));
+}
+
+// Optimally superposed (Kabsch) RMSD of x*scale+shift onto K targets, without forming the rotation:
+// rmsd^2 = (G_x + G_t - 2 lambda_max(K_Horn)) / N with the 4x4 quaternion matrix of the 3x3
+// cross-covariance (Horn 1987).  Replaces the biobox Molecule.rmsd loop of analyser.py:293-297, 665-671.
+// All sums in fp64: the result is a small difference of large numbers.
+__global__ void __launch_bounds__(256)
+rmsd_aligned_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, float scale, float shift,
+                    const float* __restrict__ targets, int N, int K, float* __restrict__ out) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    const float* t = targets + (long)k * N * 3;
+    double acc[17];  // sum x (3), sum t (3), sum |x|^2, sum |t|^2, sum x_i t_j (9)
+#pragma unroll
+    for (int i = 0; i < 17; ++i) acc[i] = 0.0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float* px = x + (long)b * sxb + (long)n * sxn;
+        double xv[3], tv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { xv[c] = (double)fmaf(px[c * sxc], scale, shift); tv[c] = (double)t[3 * n + c]; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            acc[c] += xv[c]; acc[3 + c] += tv[c];
+            acc[6] += xv[c] * xv[c]; acc[7] += tv[c] * tv[c];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) acc[8 + 3 * c + d] += xv[c] * tv[d];
+        }
+    }
+    __shared__ double red[8][17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 17; ++i) red[threadIdx.x >> 5][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[17];
+        for (int i = 0; i < 17; ++i) { s[i] = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s[i] += red[w][i]; }
+        const double n = (double)N;
+        double cx[3] = {s[0] / n, s[1] / n, s[2] / n}, ct[3] = {s[3] / n, s[4] / n, s[5] / n};
+        double gx = s[6] - n * (cx[0] * cx[0] + cx[1] * cx[1] + cx[2] * cx[2]);
+        double gt = s[7] - n * (ct[0] * ct[0] + ct[1] * ct[1] + ct[2] * ct[2]);
+        double S[3][3];
+        for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) S[c][d] = s[8 + 3 * c + d] - n * cx[c] * ct[d];
+        double Km[4][4] = {
+            {S[0][0] + S[1][1] + S[2][2], S[1][2] - S[2][1], S[2][0] - S[0][2], S[0][1] - S[1][0]},
+            {S[1][2] - S[2][1], S[0][0] - S[1][1] - S[2][2], S[0][1] + S[1][0], S[2][0] + S[0][2]},
+            {S[2][0] - S[0][2], S[0][1] + S[1][0], -S[0][0] + S[1][1] - S[2][2], S[1][2] + S[2][1]},
+            {S[0][1] - S[1][0], S[2][0] + S[0][2], S[1][2] + S[2][1], -S[0][0] - S[1][1] + S[2][2]}};
+        double lam = max_eig_sym4(Km);
+        double msd = (gx + gt - 2.0 * lam) / n;
+        out[(long)b * K + k] = (float)sqrt(fmax(msd, 0.0));
+        if (msd != msd) out[(long)b * K + k] = (float)msd;
     }
 }
 
@@ -1126,10 +1206,14 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
 }
 
 int mlp_rmsd_eval(const float* x, int64_t B, int64_t N, int64_t sxb, int64_t sxc, int64_t sxn, float scale, float shift,
-                  const float* targets, int64_t K, float* out, void* stream_) {
+                  const float* targets, int64_t K, float* out, uint32_t flags, void* stream_) {
     if (B == 0) return MLP_OK;
-    if (!x || !targets || !out || B < 0 || N <= 0 || K <= 0 || K > 65535) { mlp_set_error("mlp_rmsd_eval: bad argument"); return MLP_E_ARG; }
-    rmsd_kernel<<<dim3((unsigned)B, (unsigned)K), 256, 0, static_cast<cudaStream_t>(stream_)>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, out);
+    if (!x || !targets || !out || B < 0 || N <= 0 || K <= 0 || K > 65535 || (flags & ~MLP_RMSD_ALIGN)) { mlp_set_error("mlp_rmsd_eval: bad argument"); return MLP_E_ARG; }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (flags & MLP_RMSD_ALIGN)
+        rmsd_aligned_kernel<<<dim3((unsigned)B, (unsigned)K), 256, 0, stream>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, out);
+    else
+        rmsd_kernel<<<dim3((unsigned)B, (unsigned)K), 256, 0, stream>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, out);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { mlp_set_error(std::string("rmsd kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
     return MLP_OK;

@@ -66,6 +66,12 @@ def test_scan_error_from_target(analysis, murd_data):
     want = np.sqrt(((dec - tgt) ** 2).sum(2).mean(1)).reshape(6, 6)
     assert np.allclose(surf, want, rtol=2e-5)
     assert "RMSD_from_train_index_3" in ma.surfaces
+    del ma.surfaces["RMSD_from_train_index_3"]
+    aligned, _, _ = ma.scan_error_from_target("train", index=3)         # align=True is the reference default
+    assert np.all(aligned <= surf * (1 + 1e-5))                          # superposition can only lower the RMSD
+    del ma.surfaces["RMSD_from_train_index_3"]
+    err = ma.get_error("train", align=True)
+    assert err.shape == (16,) and np.all(err <= ma.get_error("train", align=False) * (1 + 1e-5))
     with pytest.raises(Exception):
         ma.scan_error_from_target("train")                               # 16 frames, no index
 
@@ -76,6 +82,7 @@ def test_scan_scores_and_error(analysis, murd_data):
     rows = ma.scan_scores(targets=tg)
     assert rows.shape == (36, 8)
     assert np.allclose(rows[:, 0].numpy().reshape(6, 6), ma.surfaces["Physics_bond"], rtol=1e-5)
+    ma.surfaces.pop("RMSD_from_train_index_3", None)
     assert np.allclose(rows[:, 7].numpy().reshape(6, 6), ma.scan_error_from_target("train", index=3, align=False)[0], rtol=1e-5)
     rmsd, drift, _, _ = ma.scan_error()
     assert rmsd.shape == (6, 6) and np.isfinite(rmsd).all() and np.isfinite(drift).all()
