@@ -50,9 +50,12 @@ constexpr int PF = 4;            // bonded: coordinate elements staged per threa
 constexpr int NF = 4;            // torsion Fourier orders kept (ff14SB periods are 1..4)
 constexpr int NB_T = 128;        // non-bonded tile edge (atoms)
 constexpr int NB_NI = 4;         // i-atoms per lane
-constexpr int NB_WARPS = 4;      // warps per CTA, one work item each
+#ifndef NB_WARPS_PER_CTA
+#define NB_WARPS_PER_CTA 1
+#endif
+constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each (1: a finished item frees its slot at once)
 #ifndef NB_MINB
-#define NB_MINB 4
+#define NB_MINB 4    // resident warps per SM sub-partition the register budget is sized for (4 -> 128 registers)
 #endif
 #ifndef NB_UNROLL
 #define NB_UNROLL 1
@@ -250,27 +253,30 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
               const float* __restrict__ x, long sxb, long sxc, long sxn,
               float* __restrict__ grad, long sgb, long sgc, long sgn,
               const float* __restrict__ weights, float* __restrict__ e_part /* [B][n_tiles][3] or null */,
-              int B, int conf_per_cta, uint32_t term_mask, int accumulate, int max_atoms, int stride, int max_cnt) {
+              int B, int conf_per_cta, uint32_t term_mask, int accumulate, int max_atoms, int max_cnt) {
+    constexpr int STRIDE = BT;         // slot (atom a, k-th contribution) at k*STRIDE + a
     extern __shared__ float4 smem[];
     float4* sc = smem;                 // [max_atoms] coordinates of own + halo atoms
-    float4* slots = smem + max_atoms;  // [max_cnt*stride + 1] gradient slots, slot (atom a, k) at k*stride + a; last = dump
+    float4* slots = smem + max_atoms;  // [max_cnt*STRIDE + 1] gradient slots; last = dump
     __shared__ float s_w[BT / 32][3];
 
     const BTile t = tiles[blockIdx.x];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wbase = tid & ~31;
 
-    // term records -> registers, once per CTA (lists are padded to whole warps with inert terms)
+    // term records -> registers, once per CTA (lists are padded to whole warps with inert terms).
+    // 32-term unit u of a list goes to warp (u + off) % 8, register slot u / 8; the angle and torsion
+    // lists start on different warps so that their second-round units do not pile up on warps 0..3.
     BondRec rb[RB];
     AngleRec ra[RA];
     TorsRec rt[RT];
     bool ab[RB], aa[RA], at[RT];   // warp-uniform activity flags
+    constexpr int NW = BT / 32;
 #pragma unroll
-    for (int r = 0; r < RB; ++r) { ab[r] = wbase + r * BT < t.n_bond; if (ab[r]) rb[r] = bonds[t.bond_off + tid + r * BT]; }
+    for (int r = 0; r < RB; ++r) { int i0 = (r * NW + warp) * 32; ab[r] = i0 < t.n_bond; if (ab[r]) rb[r] = bonds[t.bond_off + i0 + lane]; }
 #pragma unroll
-    for (int r = 0; r < RA; ++r) { aa[r] = wbase + r * BT < t.n_angle; if (aa[r]) ra[r] = angles[t.angle_off + tid + r * BT]; }
+    for (int r = 0; r < RA; ++r) { int i0 = (r * NW + warp) * 32; aa[r] = i0 < t.n_angle; if (aa[r]) ra[r] = angles[t.angle_off + i0 + lane]; }
 #pragma unroll
-    for (int r = 0; r < RT; ++r) { at[r] = wbase + r * BT < t.n_tors; if (at[r]) rt[r] = tors[t.tors_off + tid + r * BT]; }
+    for (int r = 0; r < RT; ++r) { int i0 = (r * NW + ((warp - NW / 2) & (NW - 1))) * 32; at[r] = i0 < t.n_tors; if (at[r]) rt[r] = tors[t.tors_off + i0 + lane]; }
     const int my_cnt = (GRAD && tid < t.n_own) ? cnts[t.cnt_off + tid] : 0;
 
     // coordinate staging plan: element e = tid + q*BT of the tile's 3*(own+halo) floats
@@ -323,7 +329,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
 #pragma unroll
         for (int q = 0; q < PF; ++q) if (sidx[q] >= 0) scf[sidx[q]] = pf[q];
         if (GRAD && term_mask != MLP_TERM_BONDED)
-            for (int s = tid; s < max_cnt * stride; s += BT) slots[s] = make_float4(0.f, 0.f, 0.f, 0.f);  // rare: a term type is off
+            for (int s = tid; s < max_cnt * STRIDE; s += BT) slots[s] = make_float4(0.f, 0.f, 0.f, 0.f);  // rare: a term type is off
         __syncthreads();
         if (b + 1 < b1) prefetch(b + 1);
 
@@ -354,12 +360,14 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
         if (GRAD && tid < t.n_own) {
             float gx = 0.f, gy = 0.f, gz = 0.f;
             const float4* col = slots + tid;
-            int k = 0;
-            for (; k + 4 <= my_cnt; k += 4) {
-                float4 v0 = col[k * stride], v1 = col[(k + 1) * stride], v2 = col[(k + 2) * stride], v3 = col[(k + 3) * stride];
+            for (int k = 0; k < my_cnt; k += 4, col += 4 * STRIDE) {   // fixed stride: immediate-offset loads
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 v0 = col[0];
+                float4 v1 = k + 1 < my_cnt ? col[STRIDE] : z;
+                float4 v2 = k + 2 < my_cnt ? col[2 * STRIDE] : z;
+                float4 v3 = k + 3 < my_cnt ? col[3 * STRIDE] : z;
                 gx += (v0.x + v1.x) + (v2.x + v3.x); gy += (v0.y + v1.y) + (v2.y + v3.y); gz += (v0.z + v1.z) + (v2.z + v3.z);
             }
-            for (; k < my_cnt; ++k) { float4 v = col[k * stride]; gx += v.x; gy += v.y; gz += v.z; }
             float* g = grad + (long)b * sgb + (long)(t.a0 + tid) * sgn;
             if (accumulate) { g[0] += gx; g[sgc] += gy; g[2 * sgc] += gz; }
             else { g[0] = gx; g[sgc] = gy; g[2 * sgc] = gz; }
@@ -513,13 +521,13 @@ __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const fl
     }
 }
 
-// One warp = one (conformation, tile pair).  Lane L owns i-atoms i0+L+32a (a<4) for the whole
+// One warp = one (conformation, tile pair).  Lane L owns i-atoms i0+4L+a (a<4) for the whole
 // tile; the 32 groups of 4 j-atoms rotate through the lanes (lane L works on group (L+r)%32 at
 // step r) together with their force accumulators, so Newton's third law costs 12 shuffles per
 // 16 pairs and no reduction.  Output: partial forces of the item's 128 i-atoms and 128 j-atoms
 // ([6][128] floats: -Fi xyz, +Fj xyz) and its energy - no atomics.
 template <bool GRAD, bool FULL>
-__global__ void __launch_bounds__(NB_WARPS * 32, NB_MINB)
+__global__ void __launch_bounds__(NB_WARPS * 32, (4 * NB_MINB) / NB_WARPS)
 nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const int2* __restrict__ pairs,
           const uint32_t* __restrict__ masks, int n_pairs, int n_masked, int Npad, int B,
           float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
@@ -542,8 +550,8 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     float3 Fi[NB_NI];
 #pragma unroll
     for (int a = 0; a < NB_NI; ++a) {
-        xi[a] = xb[i0 + lane + 32 * a];
-        pi[a] = par[i0 + lane + 32 * a];
+        xi[a] = xb[i0 + 4 * lane + a];
+        pi[a] = par[i0 + 4 * lane + a];
         Fi[a] = make_float3(0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -568,8 +576,11 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     const int src_lane = (lane + 1) & 31;
     const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m[warp]);
 
+    // Diagonal tile: block (L,g) mirrors block (g,L), so 17 of the 32 rotation steps visit every unordered
+    // block pair once (step 0 = the in-block triangle, step 16 = lanes < 16 only; the masks encode both).
+    const int n_steps = (IJ.x == IJ.y) ? 17 : 32;
 #pragma unroll 1
-    for (int r = 0; r < 32; ++r) {
+    for (int r = 0; r < n_steps; ++r) {
         const int g = (lane + r) & 31;
         float4 xj[4];
         float2 pj[4];
@@ -593,18 +604,16 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
         }
     }
     if (GRAD) {
-        // after 32 rotations lane L holds the finished forces of group L (atoms j0+4L+q);
+        // after n_steps rotations lane L holds the forces of group (L + n_steps) % 32 (atoms j0+4g+q);
         // grad_i = -sum s*(ri-rj), grad_j = +sum s*(ri-rj)   (s = -(dE/dd)/d)
         float* out = fpart + item * (6 * NB_T);
-#pragma unroll
-        for (int a = 0; a < NB_NI; ++a) {
-            out[0 * NB_T + lane + 32 * a] = -Fi[a].x;
-            out[1 * NB_T + lane + 32 * a] = -Fi[a].y;
-            out[2 * NB_T + lane + 32 * a] = -Fi[a].z;
-        }
-        reinterpret_cast<float4*>(out + 3 * NB_T)[lane] = make_float4(Fj[0].x, Fj[1].x, Fj[2].x, Fj[3].x);
-        reinterpret_cast<float4*>(out + 4 * NB_T)[lane] = make_float4(Fj[0].y, Fj[1].y, Fj[2].y, Fj[3].y);
-        reinterpret_cast<float4*>(out + 5 * NB_T)[lane] = make_float4(Fj[0].z, Fj[1].z, Fj[2].z, Fj[3].z);
+        const int gl = (lane + n_steps) & 31;
+        reinterpret_cast<float4*>(out + 0 * NB_T)[lane] = make_float4(-Fi[0].x, -Fi[1].x, -Fi[2].x, -Fi[3].x);
+        reinterpret_cast<float4*>(out + 1 * NB_T)[lane] = make_float4(-Fi[0].y, -Fi[1].y, -Fi[2].y, -Fi[3].y);
+        reinterpret_cast<float4*>(out + 2 * NB_T)[lane] = make_float4(-Fi[0].z, -Fi[1].z, -Fi[2].z, -Fi[3].z);
+        reinterpret_cast<float4*>(out + 3 * NB_T)[gl] = make_float4(Fj[0].x, Fj[1].x, Fj[2].x, Fj[3].x);
+        reinterpret_cast<float4*>(out + 4 * NB_T)[gl] = make_float4(Fj[0].y, Fj[1].y, Fj[2].y, Fj[3].y);
+        reinterpret_cast<float4*>(out + 5 * NB_T)[gl] = make_float4(Fj[0].z, Fj[1].z, Fj[2].z, Fj[3].z);
     }
     if (e_part) {
         // E = sum_lj12/12 + sum_coulomb
@@ -833,7 +842,7 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
     for (int k = 0; k < nt; ++k) if (t_live[k]) touch(2, k, &T.torsions[4 * k], 4);
     int max_cnt = 1;
     for (int a = 0; a < N; ++a) max_cnt = std::max(max_cnt, (int)inc[a].size());
-    const int stride = (std::min(tile_atoms, std::max(N, 1)) + 31) & ~31;
+    const int stride = BT;  // the kernel's compile-time slot stride
     if ((size_t)max_cnt * stride + 1 >= 0xffff) return 1;
     const uint32_t dump = (uint32_t)(max_cnt * stride);
 
@@ -967,13 +976,24 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     for (auto& kv : ex) {
         const int I = kv.first.first, J = kv.first.second;
         pairs.push_back(make_int2(I, J));
-        // uint16 [g][lane]: bit 4a+b <-> pair (i = lane+32a, j = 4g+b) allowed
+        // uint16 [g][lane]: bit 4a+b <-> pair (i = 4*lane+a, j = 4g+b) allowed
         std::vector<uint16_t> m16((size_t)32 * 32, 0xffffu);
-        auto clear = [&](int li, int lj) { m16[(size_t)(lj >> 2) * 32 + (li & 31)] &= (uint16_t)~(1u << (4 * (li >> 5) + (lj & 3))); };
-        if (I == J)
+        auto clear = [&](int li, int lj) { m16[(size_t)(lj >> 2) * 32 + (li >> 2)] &= (uint16_t)~(1u << (4 * (li & 3) + (lj & 3))); };
+        if (I == J) {
+            // keep each unordered pair in exactly one of its two blocks: the one reached in rotation steps 0..16
             for (int li = 0; li < NB_T; ++li)
-                for (int lj = 0; lj <= li; ++lj) clear(li, lj);
-        for (auto& pr : kv.second) clear(pr.first - I * NB_T, pr.second - J * NB_T);
+                for (int lj = 0; lj < NB_T; ++lj) {
+                    const int gi = li >> 2, gj = lj >> 2, dist = (gj - gi) & 31;
+                    const bool keep = (dist >= 1 && dist <= 15) || (dist == 16 && gi < 16) || (dist == 0 && li < lj);
+                    if (!keep) clear(li, lj);
+                }
+            for (auto& pr : kv.second) {  // an excluded pair may sit in either orientation
+                clear(pr.first - I * NB_T, pr.second - J * NB_T);
+                clear(pr.second - J * NB_T, pr.first - I * NB_T);
+            }
+        } else {
+            for (auto& pr : kv.second) clear(pr.first - I * NB_T, pr.second - J * NB_T);
+        }
         std::vector<uint32_t> m((size_t)NB_T * 4);
         std::memcpy(m.data(), m16.data(), m.size() * sizeof(uint32_t));
         masks.insert(masks.end(), m.begin(), m.end());
@@ -1157,11 +1177,11 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         if (grad)
             bonded_kernel<true><<<grid, BT, e->bonded_smem, stream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
                 x, sxb, sxc, sxn, grad, sgb, sgc, sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc,
-                term_mask & MLP_TERM_BONDED, accumulate, e->max_atoms, e->slot_stride, e->max_cnt);
+                term_mask & MLP_TERM_BONDED, accumulate, e->max_atoms, e->max_cnt);
         else
             bonded_kernel<false><<<grid, BT, e->bonded_smem, stream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
                 x, sxb, sxc, sxn, nullptr, 0, 0, 0, weights, energies ? e_bonded : nullptr, (int)B, cpc,
-                term_mask & MLP_TERM_BONDED, 0, e->max_atoms, e->slot_stride, e->max_cnt);
+                term_mask & MLP_TERM_BONDED, 0, e->max_atoms, e->max_cnt);
         prof_end(1);
         ++launches;
     } else if (grad && !accumulate && !nonbonded) {
