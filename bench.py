@@ -187,8 +187,9 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
     ma.set_network(net)
     ma.set_dataset("murd", data)
     targets = torch.from_numpy(frames)
-    ma.setup_grid(samples=32, padding=0.1)
-    ma.scan_scores(targets=targets)                                     # warm-up: cuDNN algorithm choice, allocator
+    warm = int(np.ceil(np.sqrt(2 * 256 * world)))                       # >= 2 full decode batches on every rank
+    ma.setup_grid(samples=warm, padding=0.1)
+    ma.scan_scores(targets=targets)                                     # warm-up: cuDNN algorithm choice, allocator, NCCL
     ma.setup_grid(samples=G, padding=0.1)
     barrier()
     t0 = time.perf_counter()
@@ -226,6 +227,78 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
             "energy_rmsd_kernels_ms_this_rank": score_ms, "energy_rmsd_share": score_ms / ms,
             "decoder": "FoldingNet AutoEncoder(out_points=2145), random init seed 0, torch default conv math (cuDNN)",
             "wall_s": time.perf_counter() - t0}
+
+
+def run_config5(dev, rank, world, info, frames, barrier, G=None):
+    """BASELINE config 5: 24 MurD tiles on a 3x3x3 lattice (N = 51 432), FoldingNet decoder of that size,
+    setup_grid(128, bounds=(-1,1,-1,1)), 4 energy terms per point, sharded + gathered."""
+    import torch.distributed as dist
+    from molearn_b200.analysis import MolearnAnalysis
+    from molearn_b200.data import CoordinateSet, tile_system
+    from molearn_b200.models import AutoEncoder
+    G = G or int(os.environ.get("MLP_CONFIG5_GRID", 128))
+    tinfo, x = tile_system(info, frames, 24, batch=1)
+    data = CoordinateSet(tinfo, x).prepare_dataset()
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    net = AutoEncoder(out_points=x.shape[1]).to(dev)
+    ma = MolearnAnalysis(batch_size=8)
+    ma.set_network(net)
+    ma.set_dataset("complex", data)
+    ma.setup_grid(samples=int(np.ceil(np.sqrt(2 * 8 * world))), bounds=(-1, 1, -1, 1), padding=0.1)
+    ma.scan_scores()                                                    # warm-up: >= 2 full decode batches per rank
+    ma.setup_grid(samples=G, bounds=(-1, 1, -1, 1), padding=0.1)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rows = ma.scan_scores()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return {"n_atoms": int(x.shape[1]), "grid": G, "value": G * G / (ms * 1e-3), "unit": "points/s", "ms": ms,
+            "n_gpus": world, "columns": int(rows.shape[1]), "gather_bytes": ma.scan_stats["gather_bytes"],
+            "finite_rows": int(torch.isfinite(rows).all(dim=1).sum()), "info": ma.physics()._dev().info()}
+
+
+def run_config2(dev, info, frames):
+    """BASELINE config 2: one Torch_Physics_Trainer training step, MurD, batch 64 (FoldingNet AE forward/backward,
+    physics loss = bonded terms of 32 interpolated decodes, AdamW update).  Reports the step time and the share of
+    the physics kernels (forward + backward correction pass), timed by CUDA events inside the C ABI."""
+    from molearn_b200.data import CoordinateSet
+    from molearn_b200.models import AutoEncoder
+    from molearn_b200.trainers import Torch_Physics_Trainer
+    data = CoordinateSet(info, frames).prepare_dataset()
+    torch.manual_seed(0)
+    tr = Torch_Physics_Trainer(device=dev)
+    tr.set_data(data)
+    tr.set_autoencoder(AutoEncoder, out_points=frames.shape[1])
+    tr.prepare_optimiser()
+    tr.prepare_physics(physics_scaling_factor=0.1)
+    batch = ((make_batch(frames, 0) - data.mean) / data.std).to(dev)
+    for _ in range(3):
+        tr.training_iteration(batch)
+    torch.cuda.synchronize()
+    dv = tr.physics_loss._dev()
+    dv.profile(True)
+    K = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        res = tr.training_iteration(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    pr = dv.profile_read()
+    dv.profile(False)
+    ms = e0.elapsed_time(e1) / K
+    phys_ms = pr["bonded"][0] / K
+    return {"ms_per_step": ms, "batch": B, "physics_conformations": B // 2, "physics_kernels_ms_per_step": phys_ms,
+            "physics_share": phys_ms / ms, "bonded_launches_per_step": pr["bonded"][1] / K,
+            "loss": float(res["loss"]), "physics_loss": float(res["physics_loss"]),
+            "note": "step time is dominated by the FoldingNet autoencoder (cuDNN); the physics loss is 2 launches"}
 
 
 def run_config4(dev, info, frames, pk):
@@ -273,6 +346,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline_bonded / scan / large-N extras")
     ap.add_argument("--scan-grid", type=int, default=256, help="G of the GxG latent grid of the scan section")
+    ap.add_argument("--config5", action="store_true", help="also run BASELINE config 5 (51 432 atoms, 128x128 scan)")
+    ap.add_argument("--config5-grid", type=int, default=128)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -372,6 +447,9 @@ def main():
     if not args.no_extras:
         out["scan"] = run_scan(dev, rank, world, info, frames, args.scan_grid, barrier)
 
+    if args.config5:
+        out["config5_50k_scan"] = run_config5(dev, rank, world, info, frames, barrier)
+
     if rank == 0:
         # ---- per-kernel durations (CUDA events on the launching stream, inside the C ABI) ----
         dv.profile(True)
@@ -414,6 +492,7 @@ def main():
                                       "conformations_per_s": BB / (t_ms * 1e-3)}
             del xb, gb, eb
         if world == 1 and not args.no_extras:
+            out["config2_training_step"] = run_config2(dev, info, frames)
             out["config4_10k_atoms"] = run_config4(dev, info, frames, pk)
         if world == 1 and not args.no_cpu_baseline:
             rate, sec, cores = cpu_port_rate(top.as_dict(), make_batch(frames, 0)[:CPU_SAMPLE], reps=5)

@@ -119,3 +119,18 @@ def test_physics_trainer_step(murd_data):
     assert gnorm > 0 and np.isfinite(gnorm)
     v = tr.valid_step(batch)
     assert torch.isfinite(v["loss"])
+
+
+def test_physics_energy_module(murd_data):
+    """[B,n,3] standardised in -> [B] energies out, differentiable (the openmm_energy call contract)."""
+    from molearn_b200.loss_functions import physics_energy
+    mod = physics_energy(murd_data.get_atominfo(), std=murd_data.std, mean=murd_data.mean, device="cuda:0",
+                         clamp={"min": -1e3, "max": 1e3})
+    x = murd_data.dataset[:3].to("cuda:0").requires_grad_(True)
+    e = mod(x)
+    assert e.shape == (3,)
+    e.nanmean().backward()
+    assert torch.isfinite(x.grad).all() and float(x.grad.abs().max()) <= 1e3 * murd_data.std / 3 + 1e-3
+    topo = load_golden("topo_bbcb")
+    want = eo.energy_all(murd_data.coords[0].astype(np.float64), topo, want_grad=False)[0].sum()
+    assert abs(float(e[0]) - want) < 2e-5 * abs(want)
