@@ -195,6 +195,20 @@ class TorchProteinEnergy:
         The non-bonded column is 0 when ``nonbonded=False``."""
         return self._energies(x, TERM_ALL if nonbonded else TERM_BONDED)
 
+    def energy_and_gradient(self, x, nonbonded=True, energies=None, grad=None):
+        """Energies ``[B, 4]`` and the gradient of their sum ``dE/dx`` (same logical shape as ``x``) in one
+        fused pass, without building an autograd graph - the call for scoring / sampling loops that consume
+        forces directly.  Optional preallocated outputs are written in place."""
+        _check_input(x, self.n_atoms)
+        x = x.detach()
+        if energies is None:
+            energies = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
+        if grad is None:
+            grad = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            self._dev().eval(x, energies, grad, None, TERM_ALL if nonbonded else TERM_BONDED)
+        return energies, grad
+
     # -- reference API ------------------------------------------------------------------------
     def get_energy(self, x, nonbonded=False):
         """torch_protein_energy.py:55-68: bonded terms are batch MEANS, the NB term a batch SUM."""
