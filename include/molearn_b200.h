@@ -175,6 +175,18 @@ int mlp_rmsd_eval(const float* x, int64_t B, int64_t N,
                   int64_t sxb, int64_t sxc, int64_t sxn, float scale, float shift,
                   const float* targets, int64_t K, float* out, uint32_t flags, void* stream);
 
+/* Per-structure geometry statistics (scan reducers scan_bondlength / scan_ca_chirality and their
+ * get_bondlengths / get_inversions helpers, analyser.py:340-473, 831-861, 980-1014).
+ *   x          dev [B,3,N] logical with strides; lengths are computed on x*scale
+ *   pairs      dev [n_pairs,2] atom indices; pair_group dev [n_pairs] group id in [0,n_groups), n_groups <= 8
+ *   quads      dev [n_quads,4] = (N, CA, C, CB) indices
+ *   out        dev [B, 2*n_groups+1] = mean and population std of the pair lengths of each group, then the
+ *              number of quadruples with a negative triple product ((n-ca)x(c-ca)).(cb-ca)
+ */
+int mlp_geometry_eval(const float* x, int64_t B, int64_t sxb, int64_t sxc, int64_t sxn, float scale,
+                      const int32_t* pairs, const int32_t* pair_group, int64_t n_pairs, int64_t n_groups,
+                      const int32_t* quads, int64_t n_quads, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,8 @@ SYMBOLS = {
     "mlp_energy_last_launches": (c_int, [c_void_p]),
     "mlp_energy_profile": (c_int, [c_void_p, c_int]),
     "mlp_energy_profile_read": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "mlp_geometry_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_int64,
+                                  c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "mlp_rmsd_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_float,
                               c_void_p, c_int64, c_void_p, c_uint32, c_void_p]),
 }

@@ -27,7 +27,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from .reducers import rmsd_to_targets
+from .reducers import GeometryStats, backbone_indices, rmsd_to_targets
 
 
 @dataclass
@@ -302,6 +302,76 @@ class MolearnAnalysis:
             return e if tg is None else torch.cat([e, rmsd_to_targets(dec, tg, self.stdval, self.meanval)], dim=1)
 
         return self._scan_rows(4 + k, score)
+
+    # -- geometry reducers (analyser.py:340-473, 980-1014) --------------------------------------------------
+    def _geometry(self):
+        if getattr(self, "_geom", None) is None:
+            if self._atominfo is None:
+                raise ValueError("geometry scans need a dataset with get_atominfo() (set_dataset first)")
+            self._geom = GeometryStats(self._atominfo, self.device)
+        return self._geom
+
+    def _structures(self, key):
+        """(dataset or None, decoded) in Angstrom on the device, like get_dataset/get_decoded(scale=True)."""
+        if key in self._datasets:
+            ds = self.get_dataset(key, scale=True)
+        elif key in self._encoded:
+            ds = None
+        else:
+            raise ValueError(f"Key {key} not found in _datasets or _encoded. Please load the dataset or setup a grid first.")
+        return ds, self.get_decoded(key, scale=True)
+
+    def get_bondlengths(self, key):
+        """Backbone bond lengths per bond and structure, ``{type: [n_bonds, F]}`` (analyser.py:418-473)."""
+        bonds, _ = backbone_indices(self._atominfo)
+
+        def lengths(crds):
+            return {k: np.array([np.linalg.norm(crds[:, i, :] - crds[:, j, :], axis=1) for i, j in v]) for k, v in bonds.items()}
+
+        ds, dec = self._structures(key)
+        out = dict(decoded_bondlen=lengths(dec.numpy()))
+        if ds is not None:
+            out["dataset_bondlen"] = lengths(ds.numpy())
+        return out
+
+    def get_inversions(self, key):
+        """Number of C-alpha chirality inversions per structure (analyser.py:340-416), computed on the device."""
+        if not {"CA", "C", "N", "CB"}.issubset(set(str(a) for a in self._atominfo[:, 0])):
+            raise ValueError("Atom selection should include CA, C, N, and CB")
+        geom = self._geometry()
+
+        def count(crds):
+            res = []
+            for slc in self._slices(crds.shape[0]):
+                res.append(geom(crds[slc].to(self.device).float())[:, -1].cpu())
+            return torch.cat(res).numpy().astype(np.int64)
+
+        ds, dec = self._structures(key)
+        out = dict(decoded_inversions=count(dec))
+        if ds is not None:
+            out["dataset_inversions"] = count(ds)
+        return out
+
+    def _scan_geometry(self):
+        if "_geometry_rows" not in self.__dict__ or self._geometry_rows_grid is not self._encoded.get("grid"):
+            geom = self._geometry()
+            self._geometry_rows = self._scan_rows(2 * len(geom.types) + 1, lambda z, dec: geom(dec, self.stdval))
+            self._geometry_rows_grid = self._encoded.get("grid")
+        return self._geometry_rows
+
+    def scan_ca_chirality(self):
+        """Surface ``"Chirality"``: number of inverted C-alpha centres per grid structure (analyser.py:980-997).
+        Fused decode -> count on the device."""
+        rows = self._scan_geometry()
+        self.surfaces["Chirality"] = self._surface(rows[:, -1]).astype(np.int64)
+
+    def scan_bondlength(self):
+        """Surfaces ``"N-CA"``, ``"N-CA_std"``, ... : mean and std of each backbone bond type per grid structure
+        (analyser.py:999-1014).  Fused decode -> statistics on the device."""
+        rows = self._scan_geometry()
+        for g, t in enumerate(self._geometry().types):
+            self.surfaces[t] = self._surface(rows[:, 2 * g])
+            self.surfaces[t + "_std"] = self._surface(rows[:, 2 * g + 1])
 
     def scan_custom(self, fct, params, key):
         """User metric on every decoded structure, host loop (analyser.py:1016-1039).  ``fct`` receives

@@ -35,3 +35,67 @@ def rmsd_to_targets(x, targets, scale: float = 1.0, shift: float = 0.0, align: b
                                             _lib.RMSD_ALIGN if align else 0,
                                             torch.cuda.current_stream(x.device).cuda_stream))
     return out
+
+
+BOND_TYPES = ("N-CA", "CA-C", "C-N", "CA-CB")
+
+
+def backbone_indices(atominfo):
+    """Atom index lists the reference builds from ``self.mol.data`` (analyser.py:357-373, 423-449): per residue (in
+    order of first appearance of its resid) the first N / CA / C / CB; ``C-N`` links a residue to resid+1.
+    Returns ``(bonds: {type: [(i, j), ...]}, quads: [(N, CA, C, CB), ...])`` - CA-CB and the chirality quadruples
+    skip GLY; types whose atoms are not selected are absent."""
+    names = [str(a) for a in atominfo[:, 0]]
+    resn = [str(a) for a in atominfo[:, 1]]
+    resid = [int(a) for a in atominfo[:, 2]]
+    atoms = set(names)
+    if not {"CA", "C", "N"}.issubset(atoms):
+        raise ValueError("Selected atoms should contain at least N, CA, and C.")
+    first = {}
+    order = []
+    for i, (a, r) in enumerate(zip(names, resid)):
+        if r not in first:
+            first[r] = {"resname": resn[i]}
+            order.append(r)
+        first[r].setdefault(a, i)
+    bonds = {"N-CA": [], "CA-C": [], "C-N": []}
+    if "CB" in atoms:
+        bonds["CA-CB"] = []
+    quads = []
+    last = max(order)
+    for r in order:
+        d = first[r]
+        bonds["N-CA"].append((d["N"], d["CA"]))
+        bonds["CA-C"].append((d["CA"], d["C"]))
+        if d["resname"] != "GLY" and "CB" in atoms:
+            bonds["CA-CB"].append((d["CA"], d["CB"]))
+            quads.append((d["N"], d["CA"], d["C"], d["CB"]))
+        if r != last:
+            bonds["C-N"].append((d["C"], first[r + 1]["N"]))
+    return bonds, quads
+
+
+class GeometryStats:
+    """Device tables + launcher of ``mlp_geometry_eval`` for one atom selection."""
+
+    def __init__(self, atominfo, device):
+        import numpy as np
+        self.bonds, self.quads = backbone_indices(atominfo)
+        self.types = [t for t in BOND_TYPES if t in self.bonds]
+        pairs = np.concatenate([np.asarray(self.bonds[t], dtype=np.int32).reshape(-1, 2) for t in self.types])
+        group = np.concatenate([np.full(len(self.bonds[t]), g, dtype=np.int32) for g, t in enumerate(self.types)])
+        self.pairs = torch.from_numpy(pairs).to(device)
+        self.group = torch.from_numpy(group).to(device)
+        self.quad_t = torch.from_numpy(np.asarray(self.quads, dtype=np.int32).reshape(-1, 4)).to(device)
+
+    def __call__(self, x, scale: float = 1.0):
+        """x [B, N, 3] CUDA float32 (any strides) -> [B, 2*G+1]: (mean, std) per bond type, then inversions."""
+        G = len(self.types)
+        out = torch.empty((x.shape[0], 2 * G + 1), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mlp_geometry_eval(
+                x.data_ptr(), x.shape[0], x.stride(0), x.stride(2), x.stride(1), float(scale),
+                self.pairs.data_ptr(), self.group.data_ptr(), self.pairs.shape[0], G,
+                self.quad_t.data_ptr() if len(self.quads) else None, len(self.quads), out.data_ptr(),
+                torch.cuda.current_stream(x.device).cuda_stream))
+        return out

@@ -784,6 +784,63 @@ rmsd_aligned_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, f
     }
 }
 
+// Per-structure geometry statistics for the scan reducers scan_bondlength / scan_ca_chirality
+// (analyser.py:340-473, 831-861, 980-1014): mean and population std of the lengths of up to 8 groups of atom
+// pairs, and the number of quadruples (n, ca, c, cb) whose triple product ((n-ca) x (c-ca)) . (cb-ca) is
+// negative.  out[b] = (mean_0, std_0, ..., mean_{G-1}, std_{G-1}, inversions).  fp64 sums.
+constexpr int GEOM_MAX_GROUPS = 8;
+__global__ void __launch_bounds__(256)
+geom_stats_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, float scale,
+                  const int2* __restrict__ pairs, const int* __restrict__ pair_group, int n_pairs, int n_groups,
+                  const int4* __restrict__ quads, int n_quads, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    const float* xb = x + (long)b * sxb;
+    auto at = [&](int n) { const float* p = xb + (long)n * sxn; return make_float3(p[0] * scale, p[sxc] * scale, p[2 * sxc] * scale); };
+    double acc[2 * GEOM_MAX_GROUPS + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * GEOM_MAX_GROUPS + 1; ++i) acc[i] = 0.0;
+    for (int k = threadIdx.x; k < n_pairs; k += blockDim.x) {
+        const int2 pr = pairs[k];
+        const int gidx = pair_group[k];
+        float3 d = at(pr.x) - at(pr.y);
+        double len = sqrt((double)d.x * d.x + (double)d.y * d.y + (double)d.z * d.z);
+#pragma unroll
+        for (int q = 0; q < GEOM_MAX_GROUPS; ++q)
+            if (q == gidx) { acc[2 * q] += len; acc[2 * q + 1] += len * len; }
+    }
+    for (int k = threadIdx.x; k < n_quads; k += blockDim.x) {
+        const int4 qd = quads[k];
+        float3 ca = at(qd.y);
+        float3 v = cross(at(qd.x) - ca, at(qd.z) - ca);
+        if (dot(v, at(qd.w) - ca) < 0.f) acc[2 * GEOM_MAX_GROUPS] += 1.0;
+    }
+    __shared__ double red[8][2 * GEOM_MAX_GROUPS + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * GEOM_MAX_GROUPS + 1; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 2 * GEOM_MAX_GROUPS + 1; ++i) red[threadIdx.x >> 5][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x <= 2 * n_groups && threadIdx.x <= 2 * GEOM_MAX_GROUPS) {
+        // thread t < 2G: statistic t of group t/2; thread 2G: inversions
+        const int t = threadIdx.x;
+        auto total = [&](int i) { double s = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][i]; return s; };
+        float* o = out + (long)b * (2 * n_groups + 1);
+        if (t == 2 * n_groups) o[t] = (float)total(2 * GEOM_MAX_GROUPS);
+        else {
+            // per-group pair counts are recomputed here (cheap) to avoid another accumulator
+            const int gq = t >> 1;
+            int cnt = 0;
+            for (int k = 0; k < n_pairs; ++k) cnt += pair_group[k] == gq;
+            double m = cnt ? total(2 * gq) / cnt : 0.0;
+            if (t & 1) { double v = cnt ? total(2 * gq + 1) / cnt - m * m : 0.0; o[t] = (float)sqrt(v > 0.0 ? v : 0.0); }
+            else o[t] = (float)m;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host: packing
 // ------------------------------------------------------------------------------------------
@@ -1236,6 +1293,23 @@ int mlp_rmsd_eval(const float* x, int64_t B, int64_t N, int64_t sxb, int64_t sxc
         rmsd_kernel<<<dim3((unsigned)B, (unsigned)K), 256, 0, stream>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, out);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { mlp_set_error(std::string("rmsd kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
+    return MLP_OK;
+}
+
+int mlp_geometry_eval(const float* x, int64_t B, int64_t sxb, int64_t sxc, int64_t sxn, float scale,
+                      const int32_t* pairs, const int32_t* pair_group, int64_t n_pairs, int64_t n_groups,
+                      const int32_t* quads, int64_t n_quads, float* out, void* stream_) {
+    if (B == 0) return MLP_OK;
+    if (!x || !out || B < 0 || n_pairs < 0 || n_quads < 0 || n_groups < 0 || n_groups > GEOM_MAX_GROUPS ||
+        (n_pairs > 0 && (!pairs || !pair_group)) || (n_quads > 0 && !quads)) {
+        mlp_set_error("mlp_geometry_eval: bad argument");
+        return MLP_E_ARG;
+    }
+    geom_stats_kernel<<<(unsigned)B, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        x, sxb, sxc, sxn, scale, reinterpret_cast<const int2*>(pairs), pair_group, (int)n_pairs, (int)n_groups,
+        reinterpret_cast<const int4*>(quads), (int)n_quads, out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { mlp_set_error(std::string("geometry kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
     return MLP_OK;
 }
 

@@ -134,3 +134,28 @@ def test_physics_energy_module(murd_data):
     topo = load_golden("topo_bbcb")
     want = eo.energy_all(murd_data.coords[0].astype(np.float64), topo, want_grad=False)[0].sum()
     assert abs(float(e[0]) - want) < 2e-5 * abs(want)
+
+
+def test_geometry_scans_vs_numpy(analysis, murd_data):
+    """scan_bondlength / scan_ca_chirality (device, fused) against the reference's NumPy formulas
+    (analyser.py:831-861) applied to the decoded structures."""
+    from molearn_b200.analysis import backbone_indices
+    ma = analysis
+    ma.scan_bondlength()
+    ma.scan_ca_chirality()
+    dec = decoded_angstrom(ma) - ma.meanval                                # the reference's scan uses decoded*std
+    bonds, quads = backbone_indices(murd_data.get_atominfo())
+    assert set(bonds) == {"N-CA", "CA-C", "C-N", "CA-CB"} and len(bonds["C-N"]) == len(bonds["N-CA"]) - 1
+    for k, v in bonds.items():
+        L = np.array([np.linalg.norm(dec[:, i, :] - dec[:, j, :], axis=1) for i, j in v])   # [n_bonds, points]
+        assert np.allclose(ma.surfaces[k].reshape(-1), L.mean(axis=0), rtol=1e-4, atol=1e-5), k
+        assert np.allclose(ma.surfaces[k + "_std"].reshape(-1), L.std(axis=0), rtol=1e-3, atol=1e-4), k
+    q = np.asarray(quads)
+    n, ca, c, cb = (dec[:, q[:, m], :] for m in range(4))
+    trip = np.einsum("bij,bij->bi", np.cross(n - ca, c - ca), cb - ca)
+    margin = np.abs(trip).min(axis=1) > 1e-6                                # ignore points with a borderline centre
+    assert np.array_equal(ma.surfaces["Chirality"].reshape(-1)[margin], (trip < 0).sum(axis=1)[margin])
+    inv = ma.get_inversions("train")
+    assert inv["dataset_inversions"].shape == (16,) and (inv["dataset_inversions"] == 0).all()   # MD frames: no D-residues
+    bl = ma.get_bondlengths("train")
+    assert abs(bl["dataset_bondlen"]["N-CA"].mean() - 1.46) < 0.03
