@@ -100,6 +100,10 @@ struct mlp_energy {
     int* d_red_list = nullptr;     // entries pair*2 + side (0: the tile is the pair's I, 1: its J)
     int last_launches = 0;
     int sm_count = 148;
+    // side stream: the (latency-bound) bonded kernel runs next to the non-bonded pair kernel
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = true;
     // optional per-kernel timing (mlp_energy_profile): events on the launching stream
     bool profile = false;
     std::vector<std::array<cudaEvent_t, 2>> pending[4];  // per kernel: (start, stop) pairs not read yet
@@ -1134,6 +1138,14 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
     if (rc == 1) { mlp_set_error("mlp_energy_create: topology too dense for the bonded tile"); rc = MLP_E_ARG; }
     if (rc == MLP_OK) rc = pack_nonbonded(E, *t);
     if (rc == MLP_OK) {
+        if (const char* env = std::getenv("MLP_NO_OVERLAP")) E->overlap = std::atoi(env) == 0;
+        if (cudaStreamCreateWithFlags(&E->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&E->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            mlp_set_error("mlp_energy_create: could not create the side stream"); rc = MLP_E_CUDA;
+        }
+    }
+    if (rc == MLP_OK) {
         cudaError_t e1 = cudaFuncSetAttribute(bonded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
         cudaError_t e2 = cudaFuncSetAttribute(bonded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
         if (e1 != cudaSuccess || e2 != cudaSuccess) { mlp_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); rc = MLP_E_CUDA; }
@@ -1152,6 +1164,9 @@ void mlp_energy_destroy(mlp_energy* e) {
     for (int k = 0; k < 4; ++k)
         for (auto& p : e->pending[k]) { cudaEventDestroy(p[0]); cudaEventDestroy(p[1]); }
     for (void* p : e->allocs) cudaFree(p);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side) cudaStreamDestroy(e->side);
     cudaSetDevice(prev);
     delete e;
 }
@@ -1227,20 +1242,31 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     };
     auto prof_end = [&](int k) { if (e->profile) cudaEventRecord(e->pending[k].back()[1], stream); };
 
+    // With both parts requested the bonded kernel goes to the handle's side stream (fork after everything
+    // already queued on `stream`, join before the first kernel that touches the gradient again): it is
+    // latency-bound at small batches and fills the pair kernel's tail.  Per-kernel timing keeps one stream.
+    const bool fork = bonded && nonbonded && e->overlap && !e->profile;
+    cudaStream_t bstream = stream;
+    if (fork) {
+        CK(cudaEventRecord(e->ev_fork, stream));
+        CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+        bstream = e->side;
+    }
     if (bonded) {
         prof_begin(1);
         int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
         dim3 grid(e->n_tiles, (unsigned)((B + cpc - 1) / cpc));
         if (grad)
-            bonded_kernel<true><<<grid, BT, e->bonded_smem, stream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
+            bonded_kernel<true><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
                 x, sxb, sxc, sxn, grad, sgb, sgc, sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc,
                 term_mask & MLP_TERM_BONDED, accumulate, e->max_atoms, e->max_cnt);
         else
-            bonded_kernel<false><<<grid, BT, e->bonded_smem, stream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
+            bonded_kernel<false><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
                 x, sxb, sxc, sxn, nullptr, 0, 0, 0, weights, energies ? e_bonded : nullptr, (int)B, cpc,
                 term_mask & MLP_TERM_BONDED, 0, e->max_atoms, e->max_cnt);
         prof_end(1);
         ++launches;
+        if (fork) CK(cudaEventRecord(e->ev_join, e->side));
     } else if (grad && !accumulate && !nonbonded) {
         long n = (long)B * N * 3;
         zero_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad, sgb, sgc, sgn, N, (int)B);
@@ -1263,6 +1289,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
 #undef NB_LAUNCH
         prof_end(2);
         ++launches;
+        if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient
         if (grad) {
             prof_begin(3);
             nb_reduce_kernel<<<dim3(e->n_nbt, (unsigned)B), NB_T, 0, stream>>>(fpart, e->d_red_off, e->d_red_list, e->n_pairs, N,
