@@ -92,7 +92,7 @@ struct mlp_energy {
     // non-bonded
     int n_nbt = 0;                 // tiles per edge
     int n_pairs = 0, n_masked = 0; // tile pairs (masked ones first)
-    int2* d_pairs = nullptr;       // (I,J)
+    int4* d_pairs = nullptr;       // (I, J, mask index or -1, rotation steps), longest items first
     uint32_t* d_masks = nullptr;   // [n_masked][32 groups][32 lanes] uint16 pair masks
     float* d_q = nullptr;          // [Npad]
     float2* d_par = nullptr;       // [Npad] (R/2, sqrt(12 eps))
@@ -460,13 +460,22 @@ __device__ __noinline__ float3 nb_pair_fix(float r2, float Rij, float e12, float
 // One micro-tile: NB_NI i-atoms (registers) x 4 j-atoms, fast path with clamped distance.
 // m16: bit (4a+b) = pair allowed (MASKED tiles).  Returns true if any allowed pair is closer than
 // sqrt(NB_THR2) or not comparable (NaN coordinates) - the caller then runs the exact correction.
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // sm_100 three-input min (one FMNMX3); NaN wins
+    return r;
+}
+
 template <bool MASKED, bool FULL>
 __device__ __forceinline__ bool nb_micro(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
                                           const float2 (&pj)[4], uint32_t m16,
                                           float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
-    bool close = false;
+    // smallest r^2 over the allowed pairs, two pairs per instruction; a NaN distance makes it NaN, which fails
+    // the comparison below and sends the micro-tile to the exact path (where NaN propagates)
+    float rmin = 3.0e38f;
 #pragma unroll
     for (int a = 0; a < NB_NI; ++a) {
+        float r2s[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             float dx = xi[a].x - xj[b].x, dy = xi[a].y - xj[b].y, dz = xi[a].z - xj[b].z;
@@ -480,13 +489,15 @@ __device__ __forceinline__ bool nb_micro(const float4 (&xi)[NB_NI], const float2
                 e12 = on ? e12 : 0.f;
                 qq = on ? qq : 0.f;
             }
-            close = close || !(r2 >= NB_THR2);
+            r2s[b] = r2;
             float s = nb_pair_fast<FULL>(fmaxf(r2, NB_THR2), Rij, e12, qq, Sl, Sc);
             Fi[a].x = fmaf(s, dx, Fi[a].x); Fi[a].y = fmaf(s, dy, Fi[a].y); Fi[a].z = fmaf(s, dz, Fi[a].z);
             Fj[b].x = fmaf(s, dx, Fj[b].x); Fj[b].y = fmaf(s, dy, Fj[b].y); Fj[b].z = fmaf(s, dz, Fj[b].z);
         }
+        rmin = fmin3(rmin, r2s[0], r2s[1]);
+        rmin = fmin3(rmin, r2s[2], r2s[3]);
     }
-    return close;
+    return !(rmin >= NB_THR2);
 }
 
 // Correction pass over a micro-tile that holds at least one pair closer than sqrt(NB_THR2).
@@ -532,22 +543,25 @@ __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const fl
 // ([6][128] floats: -Fi xyz, +Fj xyz) and its energy - no atomics.
 template <bool GRAD, bool FULL>
 __global__ void __launch_bounds__(NB_WARPS * 32, (4 * NB_MINB) / NB_WARPS)
-nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const int2* __restrict__ pairs,
-          const uint32_t* __restrict__ masks, int n_pairs, int n_masked, int Npad, int B,
+nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const int4* __restrict__ pairs,
+          const uint32_t* __restrict__ masks, int n_pairs, int Npad, int B,
           float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
     // j tile, group-minor: atom 4g+b lives at [b*32+g] so that lanes (different g) never conflict
     __shared__ float4 s_xj[NB_WARPS][NB_T];
     __shared__ float2 s_pj[NB_WARPS][NB_T];
     __shared__ uint32_t s_m[NB_WARPS][NB_T * 4];   // uint16 [g][lane] pair masks, as words
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long item = (long)blockIdx.x * NB_WARPS + warp;
-    if (item >= (long)B * n_pairs) return;
-    const int b = (int)(item / n_pairs), p = (int)(item - (long)b * n_pairs);
+    // work order: tile pair major, conformation minor; the pair list is sorted longest first (band tiles,
+    // clean tiles, then the half-length diagonal tiles), so the grid ends with the short items
+    const long work = (long)blockIdx.x * NB_WARPS + warp;
+    if (work >= (long)B * n_pairs) return;
+    const int p = (int)(work / B), b = (int)(work - (long)p * B);
     if (weights && !e_part && weights[4 * b + 3] == 0.f) return;  // backward correction with nothing to add (nb_reduce skips it too)
-    const int2 IJ = pairs[p];
+    const int4 IJ = pairs[p];                                       // (I, J, mask index or -1, rotation steps)
+    const long item = (long)b * n_pairs + p;                        // slot in the partial buffers
     const int i0 = IJ.x * NB_T, j0 = IJ.y * NB_T;
     const float4* xb = xq + (long)b * Npad;
-    const bool masked = p < n_masked;
+    const bool masked = IJ.z >= 0;
 
     float4 xi[NB_NI];
     float2 pi[NB_NI];
@@ -566,7 +580,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
         s_pj[warp][slot] = par[j0 + jj];
     }
     if (masked) {
-        const uint4* src = reinterpret_cast<const uint4*>(masks + (long)p * (NB_T * 4));
+        const uint4* src = reinterpret_cast<const uint4*>(masks + (long)IJ.z * (NB_T * 4));
         uint4* dst = reinterpret_cast<uint4*>(s_m[warp]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = src[lane + 32 * k];
@@ -582,7 +596,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
 
     // Diagonal tile: block (L,g) mirrors block (g,L), so 17 of the 32 rotation steps visit every unordered
     // block pair once (step 0 = the in-block triangle, step 16 = lanes < 16 only; the masks encode both).
-    const int n_steps = (IJ.x == IJ.y) ? 17 : 32;
+    const int n_steps = IJ.w;
 #pragma unroll 1
     for (int r = 0; r < n_steps; ++r) {
         const int g = (lane + r) & 31;
@@ -1032,11 +1046,10 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
         ex[{i / NB_T, j / NB_T}].push_back({i, j});
     }
     for (int t = 0; t < nt; ++t) ex[{t, t}];  // diagonal tiles are always masked (j > i)
-    std::vector<int2> pairs;
+    std::vector<int4> band, clean, diag;
     std::vector<uint32_t> masks;
     for (auto& kv : ex) {
         const int I = kv.first.first, J = kv.first.second;
-        pairs.push_back(make_int2(I, J));
         // uint16 [g][lane]: bit 4a+b <-> pair (i = 4*lane+a, j = 4g+b) allowed
         std::vector<uint16_t> m16((size_t)32 * 32, 0xffffu);
         auto clear = [&](int li, int lj) { m16[(size_t)(lj >> 2) * 32 + (li >> 2)] &= (uint16_t)~(1u << (4 * (li & 3) + (lj & 3))); };
@@ -1055,14 +1068,19 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
         } else {
             for (auto& pr : kv.second) clear(pr.first - I * NB_T, pr.second - J * NB_T);
         }
+        const int mi = (int)(masks.size() / (NB_T * 4));
         std::vector<uint32_t> m((size_t)NB_T * 4);
         std::memcpy(m.data(), m16.data(), m.size() * sizeof(uint32_t));
         masks.insert(masks.end(), m.begin(), m.end());
+        (I == J ? diag : band).push_back(make_int4(I, J, mi, I == J ? 17 : 32));
     }
-    E->n_masked = (int)pairs.size();
+    E->n_masked = (int)(band.size() + diag.size());
     for (int I = 0; I < nt; ++I)
         for (int J = I; J < nt; ++J)
-            if (!ex.count({I, J})) pairs.push_back(make_int2(I, J));
+            if (!ex.count({I, J})) clean.push_back(make_int4(I, J, -1, 32));
+    std::vector<int4> pairs(band);
+    pairs.insert(pairs.end(), clean.begin(), clean.end());
+    pairs.insert(pairs.end(), diag.begin(), diag.end());
     E->n_pairs = (int)pairs.size();
     // per tile: the partial-force blocks to sum (pair index order, i-side before j-side)
     std::vector<std::vector<int>> lists(nt);
@@ -1283,7 +1301,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         unsigned blocks = (unsigned)((items + NB_WARPS - 1) / NB_WARPS);
         const bool full = e->nb_mode == MLP_NB_FULL;
         double* ep = energies ? e_nb : nullptr;
-#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(xq, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, e->n_masked, e->Npad, (int)B, fpart, weights, ep)
+#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(xq, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, e->Npad, (int)B, fpart, weights, ep)
         if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
         else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
 #undef NB_LAUNCH
