@@ -346,6 +346,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline_bonded / scan / large-N extras")
     ap.add_argument("--scan-grid", type=int, default=256, help="G of the GxG latent grid of the scan section")
+    ap.add_argument("--bonded-only", action="store_true", help="tuning aid: only the headline + roofline_bonded sections")
     ap.add_argument("--config5", action="store_true", help="also run BASELINE config 5 (51 432 atoms, 128x128 scan)")
     ap.add_argument("--config5-grid", type=int, default=128)
     args = ap.parse_args()
@@ -523,7 +524,7 @@ def main():
     }
 
     # ---- latent-grid scan (BASELINE config 3): sharded over the ranks, one all-gather --------------
-    if not args.no_extras:
+    if not args.no_extras and not args.bonded_only:
         out["scan"] = run_scan(dev, rank, world, info, frames, args.scan_grid, barrier)
 
     if args.config5:
@@ -570,7 +571,7 @@ def main():
                                       "traffic": None, "algorithmic_bytes_per_launch": byts, "kernel_ms": t_ms,
                                       "conformations_per_s": BB / (t_ms * 1e-3)}
             del xb, gb, eb
-        if world == 1 and not args.no_extras:
+        if world == 1 and not args.no_extras and not args.bonded_only:
             out["config2_training_step"] = run_config2(dev, info, frames)
             out["config4_10k_atoms"] = run_config4(dev, info, frames, pk)
         if world == 1 and not args.no_cpu_baseline:

@@ -54,6 +54,9 @@ constexpr int NB_NI = 4;         // i-atoms per lane
 #define NB_WARPS_PER_CTA 1
 #endif
 constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each (1: a finished item frees its slot at once)
+#ifndef BONDED_MINB
+#define BONDED_MINB 2   // bonded CTAs per SM the register budget is sized for
+#endif
 #ifndef NB_MINB
 #define NB_MINB 4    // resident warps per SM sub-partition the register budget is sized for (4 -> 128 registers)
 #endif
@@ -82,6 +85,7 @@ struct mlp_energy {
     int N = 0, Npad = 0;
     // bonded
     int n_tiles = 0, tile_atoms = 0, slot_stride = 0, max_cnt = 0, max_atoms = 0;
+    bool torsion_sines = false;    // some torsion phase is not 0 / pi: the kernel keeps the sine coefficients
     BTile* d_tiles = nullptr;
     int* d_halo = nullptr;
     BondRec* d_bonds = nullptr;
@@ -209,7 +213,9 @@ __device__ __forceinline__ void angle_term(const float4* sc, float4* slots, cons
 
 // phi = atan2(b2.(c32 x c12), |b2| c12.c32), E = sum_p (V/f)(1+cos(n phi - gamma))   (:295-304)
 // evaluated as a Fourier series in (cos phi, sin phi) - no atan2 / cos calls.
-template <bool GRAD>
+// SG: the series has sine coefficients (phases other than 0 / pi).  ff14SB has none, so the usual
+// instantiation drops them (8 instructions and 8 registers per torsion).
+template <bool GRAD, bool SG>
 __device__ __forceinline__ void torsion_term(const float4* sc, float4* slots, const TorsRec& r, float w, float& e) {
     const uint32_t i = r.ij & 0x7fffu, j = r.ij >> 16, k = r.kl & 0xffffu, l = r.kl >> 16;
     float3 rj = f3(sc[j]), rk = f3(sc[k]);
@@ -227,8 +233,13 @@ __device__ __forceinline__ void torsion_term(const float4* sc, float4* slots, co
     float en = r.c0, de = 0.f;  // de = dE/dphi
 #pragma unroll
     for (int n = 1; n <= NF; ++n) {
-        en = fmaf(r.cg[n - 1], cn, fmaf(r.sg[n - 1], sn, en));
-        if (GRAD) de = fmaf((float)n, fmaf(r.sg[n - 1], cn, -r.cg[n - 1] * sn), de);
+        if (SG) {
+            en = fmaf(r.cg[n - 1], cn, fmaf(r.sg[n - 1], sn, en));
+            if (GRAD) de = fmaf((float)n, fmaf(r.sg[n - 1], cn, -r.cg[n - 1] * sn), de);
+        } else {
+            en = fmaf(r.cg[n - 1], cn, en);
+            if (GRAD) de = fmaf(-(float)n * r.cg[n - 1], sn, de);
+        }
         if (n < NF) {
             float c2 = fmaf(cn, c1, -sn * s1);
             sn = fmaf(sn, c1, cn * s1);
@@ -250,8 +261,8 @@ __device__ __forceinline__ void torsion_term(const float4* sc, float4* slots, co
     }
 }
 
-template <bool GRAD>
-__global__ void __launch_bounds__(BT, 2)
+template <bool GRAD, bool SG>
+__global__ void __launch_bounds__(BT, BONDED_MINB)
 bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, const BondRec* __restrict__ bonds,
               const AngleRec* __restrict__ angles, const TorsRec* __restrict__ tors, const int* __restrict__ cnts,
               const float* __restrict__ x, long sxb, long sxc, long sxn,
@@ -262,7 +273,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
     extern __shared__ float4 smem[];
     float4* sc = smem;                 // [max_atoms] coordinates of own + halo atoms
     float4* slots = smem + max_atoms;  // [max_cnt*STRIDE + 1] gradient slots; last = dump
-    __shared__ float s_w[BT / 32][3];
+    __shared__ float s_e[3][BT];
 
     const BTile t = tiles[blockIdx.x];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -282,6 +293,11 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
 #pragma unroll
     for (int r = 0; r < RT; ++r) { int i0 = (r * NW + ((warp - NW / 2) & (NW - 1))) * 32; at[r] = i0 < t.n_tors; if (at[r]) rt[r] = tors[t.tors_off + i0 + lane]; }
     const int my_cnt = (GRAD && tid < t.n_own) ? cnts[t.cnt_off + tid] : 0;
+    const int wcnt = (__reduce_max_sync(0xffffffffu, my_cnt) + 3) & ~3;   // <= max_cnt (a multiple of 4)
+    if (GRAD) {
+        for (int s = tid; s < max_cnt * STRIDE; s += BT) slots[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ordered before the first slot write by the first __syncthreads of the conformation loop
+    }
 
     // coordinate staging plan: element e = tid + q*BT of the tile's 3*(own+halo) floats
     long goff[PF];
@@ -348,33 +364,32 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
         }
         if (do_t) {
 #pragma unroll
-            for (int r = 0; r < RT; ++r) if (at[r]) torsion_term<GRAD>(sc, slots, rt[r], wt, et);
+            for (int r = 0; r < RT; ++r) if (at[r]) torsion_term<GRAD, SG>(sc, slots, rt[r], wt, et);
         }
-        if (e_part) {
-            eb = warp_sum(eb); ea = warp_sum(ea); et = warp_sum(et);
-            if (lane == 0) { s_w[warp][0] = eb; s_w[warp][1] = ea; s_w[warp][2] = et; }
-        }
+        if (e_part) { s_e[0][tid] = eb; s_e[1][tid] = ea; s_e[2][tid] = et; }
         __syncthreads();
-        if (e_part && tid < 3) {
+        if (e_part && warp < 3) {
+            // warp w sums term w over the CTA in a fixed order (reproducible); the other warps go on
             float s = 0.f;
 #pragma unroll
-            for (int k = 0; k < BT / 32; ++k) s += s_w[k][tid];     // fixed order: reproducible
-            e_part[((long)b * gridDim.x + blockIdx.x) * 3 + tid] = s;
+            for (int k = 0; k < BT / 32; ++k) s += s_e[warp][lane + 32 * k];
+            s = warp_sum(s);
+            if (lane == 0) e_part[((long)b * gridDim.x + blockIdx.x) * 3 + warp] = s;
         }
-        if (GRAD && tid < t.n_own) {
+        if (GRAD) {
+            // per-atom column sum; the bound is warp-uniform and a multiple of 4: slots past an atom's own
+            // count are never written by any term and hold the zeros stored at kernel start
             float gx = 0.f, gy = 0.f, gz = 0.f;
             const float4* col = slots + tid;
-            for (int k = 0; k < my_cnt; k += 4, col += 4 * STRIDE) {   // fixed stride: immediate-offset loads
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 v0 = col[0];
-                float4 v1 = k + 1 < my_cnt ? col[STRIDE] : z;
-                float4 v2 = k + 2 < my_cnt ? col[2 * STRIDE] : z;
-                float4 v3 = k + 3 < my_cnt ? col[3 * STRIDE] : z;
+            for (int k = 0; k < wcnt; k += 4, col += 4 * STRIDE) {      // fixed stride: immediate-offset loads
+                float4 v0 = col[0], v1 = col[STRIDE], v2 = col[2 * STRIDE], v3 = col[3 * STRIDE];
                 gx += (v0.x + v1.x) + (v2.x + v3.x); gy += (v0.y + v1.y) + (v2.y + v3.y); gz += (v0.z + v1.z) + (v2.z + v3.z);
             }
-            float* g = grad + (long)b * sgb + (long)(t.a0 + tid) * sgn;
-            if (accumulate) { g[0] += gx; g[sgc] += gy; g[2 * sgc] += gz; }
-            else { g[0] = gx; g[sgc] = gy; g[2 * sgc] = gz; }
+            if (tid < t.n_own) {
+                float* g = grad + (long)b * sgb + (long)(t.a0 + tid) * sgn;
+                if (accumulate) { g[0] += gx; g[sgc] += gy; g[2 * sgc] += gz; }
+                else { g[0] = gx; g[sgc] = gy; g[2 * sgc] = gz; }
+            }
         }
         // the next iteration's staging only touches sc (term phase done); its slot writes happen after the
         // next barrier, i.e. after every gather above.
@@ -902,6 +917,8 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
             sg[n - 1] += amp * std::sin(ph);
         }
         t_live[k] = live;
+        for (int n = 0; n < NF; ++n)   // sin(fp32(pi)) = -8.7e-8: below 1e-6 of the cosine coefficient it is rounding noise
+            if (std::fabs(sg[n]) > 1e-6 * std::max(std::fabs(cg[n]), 1e-30)) E->torsion_sines = true;
         t_coef[k][0] = (float)c0;
         for (int n = 0; n < NF; ++n) { t_coef[k][1 + n] = (float)cg[n]; t_coef[k][1 + NF + n] = (float)sg[n]; }
     }
@@ -917,10 +934,12 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
     for (int k = 0; k < nt; ++k) if (t_live[k]) touch(2, k, &T.torsions[4 * k], 4);
     int max_cnt = 1;
     for (int a = 0; a < N; ++a) max_cnt = std::max(max_cnt, (int)inc[a].size());
+    max_cnt = (max_cnt + 3) & ~3;   // the gather reads whole groups of 4 slots
     const int stride = BT;  // the kernel's compile-time slot stride
     if ((size_t)max_cnt * stride + 1 >= 0xffff) return 1;
     const uint32_t dump = (uint32_t)(max_cnt * stride);
 
+    if (const char* env = std::getenv("MLP_FORCE_TORSION_SINES")) if (std::atoi(env)) E->torsion_sines = true;  // test hook
     std::vector<BTile> tiles;
     std::vector<int> halo_all, cnt_all;
     std::vector<BondRec> bonds_all;
@@ -1164,8 +1183,10 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
         }
     }
     if (rc == MLP_OK) {
-        cudaError_t e1 = cudaFuncSetAttribute(bonded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
-        cudaError_t e2 = cudaFuncSetAttribute(bonded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
+        cudaError_t e1 = cudaFuncSetAttribute(bonded_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
+        cudaError_t e2 = cudaFuncSetAttribute(bonded_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(bonded_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
+        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(bonded_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
         if (e1 != cudaSuccess || e2 != cudaSuccess) { mlp_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); rc = MLP_E_CUDA; }
     }
     cudaSetDevice(prev);
@@ -1274,14 +1295,12 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         prof_begin(1);
         int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
         dim3 grid(e->n_tiles, (unsigned)((B + cpc - 1) / cpc));
-        if (grad)
-            bonded_kernel<true><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
-                x, sxb, sxc, sxn, grad, sgb, sgc, sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc,
-                term_mask & MLP_TERM_BONDED, accumulate, e->max_atoms, e->max_cnt);
-        else
-            bonded_kernel<false><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt,
-                x, sxb, sxc, sxn, nullptr, 0, 0, 0, weights, energies ? e_bonded : nullptr, (int)B, cpc,
-                term_mask & MLP_TERM_BONDED, 0, e->max_atoms, e->max_cnt);
+#define BONDED_LAUNCH(G, S) bonded_kernel<G, S><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt, \
+            x, sxb, sxc, sxn, grad, sgb, sgc, sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc, \
+            term_mask & MLP_TERM_BONDED, grad ? (int)accumulate : 0, e->max_atoms, e->max_cnt)
+        if (grad) { if (e->torsion_sines) BONDED_LAUNCH(true, true); else BONDED_LAUNCH(true, false); }
+        else { if (e->torsion_sines) BONDED_LAUNCH(false, true); else BONDED_LAUNCH(false, false); }
+#undef BONDED_LAUNCH
         prof_end(1);
         ++launches;
         if (fork) CK(cudaEventRecord(e->ev_join, e->side));

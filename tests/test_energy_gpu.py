@@ -219,3 +219,20 @@ def test_large_batch_properties(dev, energy_objs, golden_energy):
     eb = tpe.energy_per_conformation(big)
     assert torch.equal(eb.view(64, 64, 4)[0], eb.view(64, 64, 4)[63])
     assert torch.allclose(eb.view(64, 64, 4).double().sum(0), 64 * e.double(), rtol=1e-6)
+
+
+def test_general_torsion_phase_kernel(dev, golden_topo, golden_energy, monkeypatch):
+    """ff14SB has only 0 / pi phases, so the product instantiates the cosine-only torsion series; the general
+    (sine + cosine) instantiation is forced here and must give the same answers."""
+    from molearn_b200 import TorchProteinEnergy
+    monkeypatch.setenv("MLP_FORCE_TORSION_SINES", "1")
+    tpe = TorchProteinEnergy(None, atominfo_from(golden_topo("bbcb")), device=dev)
+    en = golden_energy("bbcb")
+    gf = list(en["grad_frames"])
+    x = torch.from_numpy(en["x"][gf]).to(dev).permute(0, 2, 1).requires_grad_(True)
+    e = tpe.energy_per_conformation(x)
+    e[:, 2].sum().backward()
+    got = x.grad.permute(0, 2, 1).double().cpu().numpy()
+    for q, f in enumerate(gf):
+        assert abs(float(e[q, 2]) - en["e64"][f, 2]) < TOL * en["e64"][f, 2]
+        assert rel(got[q], en["g64"][q, 2]) < TOL
