@@ -399,22 +399,16 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
 // ------------------------------------------------------------------------------------------
 // non-bonded kernels
 // ------------------------------------------------------------------------------------------
-// gather x (any strides) into [B][Npad] float4 (x,y,z,q); padding atoms are parked far away with
-// zero charge / epsilon so that they contribute exactly 0 without any test in the pair loop.
-__global__ void nb_pack_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float* __restrict__ q,
-                               float4* __restrict__ xq, int N, int Npad, int B) {
-    // (conformations whose upstream NB weight is 0 are packed too: 28 B per atom, not worth a test)
-    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)B * Npad) return;
-    int b = (int)(idx / Npad), n = (int)(idx - (long)b * Npad);
-    float4 v;
+// Atom n of a conformation as (x, y, z, q), read from the caller's tensor with its own strides (the batch
+// dimension is already applied to xb).  Atoms past N pad the last 128-atom tile: they are parked far away
+// with zero charge / epsilon so that they contribute exactly 0 without any test in the pair loop.
+__device__ __forceinline__ float4 nb_load_atom(const float* __restrict__ xb, long sxc, long sxn,
+                                               const float* __restrict__ q, int n, int N) {
     if (n < N) {
-        const float* p = x + (long)b * sxb + (long)n * sxn;
-        v = make_float4(p[0], p[sxc], p[2 * sxc], q[n]);
-    } else {
-        v = make_float4(1.0e6f + 100.f * (float)(n - N), -1.0e6f, 1.0e6f, 0.f);
+        const float* p = xb + (long)n * sxn;
+        return make_float4(p[0], p[sxc], p[2 * sxc], q[n]);
     }
-    xq[idx] = v;
+    return make_float4(1.0e6f + 100.f * (float)(n - N), -1.0e6f, 1.0e6f, 0.f);
 }
 
 __device__ __forceinline__ void warp_fn(float d, float k, float& w, float& dw) {
@@ -558,8 +552,9 @@ __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const fl
 // ([6][128] floats: -Fi xyz, +Fj xyz) and its energy - no atomics.
 template <bool GRAD, bool FULL>
 __global__ void __launch_bounds__(NB_WARPS * 32, (4 * NB_MINB) / NB_WARPS)
-nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const int4* __restrict__ pairs,
-          const uint32_t* __restrict__ masks, int n_pairs, int Npad, int B,
+nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float* __restrict__ q, int N,
+          const float2* __restrict__ par, const int4* __restrict__ pairs,
+          const uint32_t* __restrict__ masks, int n_pairs, int B,
           float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
     // j tile, group-minor: atom 4g+b lives at [b*32+g] so that lanes (different g) never conflict
     __shared__ float4 s_xj[NB_WARPS][NB_T];
@@ -575,7 +570,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     const int4 IJ = pairs[p];                                       // (I, J, mask index or -1, rotation steps)
     const long item = (long)b * n_pairs + p;                        // slot in the partial buffers
     const int i0 = IJ.x * NB_T, j0 = IJ.y * NB_T;
-    const float4* xb = xq + (long)b * Npad;
+    const float* xb = x + (long)b * sxb;
     const bool masked = IJ.z >= 0;
 
     float4 xi[NB_NI];
@@ -583,7 +578,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     float3 Fi[NB_NI];
 #pragma unroll
     for (int a = 0; a < NB_NI; ++a) {
-        xi[a] = xb[i0 + 4 * lane + a];
+        xi[a] = nb_load_atom(xb, sxc, sxn, q, i0 + 4 * lane + a, N);
         pi[a] = par[i0 + 4 * lane + a];
         Fi[a] = make_float3(0.f, 0.f, 0.f);
     }
@@ -591,7 +586,7 @@ nb_kernel(const float4* __restrict__ xq, const float2* __restrict__ par, const i
     for (int k = 0; k < NB_T / 32; ++k) {
         int jj = lane + 32 * k;
         int slot = (jj & 3) * 32 + (jj >> 2);
-        s_xj[warp][slot] = xb[j0 + jj];
+        s_xj[warp][slot] = nb_load_atom(xb, sxc, sxn, q, j0 + jj, N);
         s_pj[warp][slot] = par[j0 + jj];
     }
     if (masked) {
@@ -672,7 +667,20 @@ nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_of
     }
     float sx = 0.f, sy = 0.f, sz = 0.f;
     const float* base = fpart + (long)b * n_pairs * (6 * NB_T) + l;
-    for (int k = red_off[T]; k < red_off[T + 1]; ++k) {
+    const int k0 = red_off[T], k1 = red_off[T + 1];
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {   // four independent block loads in flight; the order of the adds is fixed
+        float vx[4], vy[4], vz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = red_list[k + u];
+            const float* p = base + (long)(e >> 1) * (6 * NB_T) + (e & 1) * (3 * NB_T);
+            vx[u] = p[0]; vy[u] = p[NB_T]; vz[u] = p[2 * NB_T];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sx += vx[u]; sy += vy[u]; sz += vz[u]; }
+    }
+    for (; k < k1; ++k) {
         const int e = red_list[k];
         const float* p = base + (long)(e >> 1) * (6 * NB_T) + (e & 1) * (3 * NB_T);
         sx += p[0]; sy += p[NB_T]; sz += p[2 * NB_T];
@@ -1122,7 +1130,7 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     return MLP_OK;
 }
 
-struct Workspace { size_t e_bonded, e_nb, xq, fpart, total; };
+struct Workspace { size_t e_bonded, e_nb, fpart, total; };
 
 Workspace layout(const mlp_energy* e, int64_t B, uint32_t term_mask, bool grad) {
     Workspace w{};
@@ -1130,8 +1138,6 @@ Workspace layout(const mlp_energy* e, int64_t B, uint32_t term_mask, bool grad) 
     w.e_bonded = off; off += align256((size_t)B * std::max(e->n_tiles, 1) * 3 * sizeof(float));
     w.e_nb = off;
     if (term_mask & MLP_TERM_NB) off += align256((size_t)B * e->n_pairs * sizeof(double));
-    w.xq = off;
-    if (term_mask & MLP_TERM_NB) off += align256((size_t)B * e->Npad * sizeof(float4));
     w.fpart = off;
     if ((term_mask & MLP_TERM_NB) && grad) off += align256((size_t)B * e->n_pairs * 6 * NB_T * sizeof(float));
     w.total = off + 256;
@@ -1265,7 +1271,6 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
     float* e_bonded = reinterpret_cast<float*>(ws + W.e_bonded);
     double* e_nb = reinterpret_cast<double*>(ws + W.e_nb);
-    float4* xq = reinterpret_cast<float4*>(ws + W.xq);
     float* fpart = reinterpret_cast<float*>(ws + W.fpart);
     const int N = e->N;
     const bool accumulate = flags & MLP_EVAL_ACCUMULATE_GRAD;
@@ -1285,6 +1290,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     // already queued on `stream`, join before the first kernel that touches the gradient again): it is
     // latency-bound at small batches and fills the pair kernel's tail.  Per-kernel timing keeps one stream.
     const bool fork = bonded && nonbonded && e->overlap && !e->profile;
+    bool finalize_on_side = false;
     cudaStream_t bstream = stream;
     if (fork) {
         CK(cudaEventRecord(e->ev_fork, stream));
@@ -1310,23 +1316,27 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         ++launches;
     }
     if (nonbonded) {
-        long n = (long)B * e->Npad;
-        prof_begin(0);
-        nb_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, xq, N, e->Npad, (int)B);
-        prof_end(0);
-        ++launches;
         prof_begin(2);
         long items = (long)B * e->n_pairs;
         unsigned blocks = (unsigned)((items + NB_WARPS - 1) / NB_WARPS);
         const bool full = e->nb_mode == MLP_NB_FULL;
         double* ep = energies ? e_nb : nullptr;
-#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(xq, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, e->Npad, (int)B, fpart, weights, ep)
+#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
         if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
         else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
 #undef NB_LAUNCH
         prof_end(2);
         ++launches;
         if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient
+        if (fork && energies && grad) {
+            // the energy sums only need the two kernels' partials: run them next to the force reduction
+            CK(cudaEventRecord(e->ev_fork, stream));
+            CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+            finalize_kernel<<<(unsigned)B, 128, 0, e->side>>>(e_bonded, e->n_tiles, e_nb, e->n_pairs, energies, term_mask);
+            CK(cudaEventRecord(e->ev_join, e->side));
+            finalize_on_side = true;
+            ++launches;
+        }
         if (grad) {
             prof_begin(3);
             nb_reduce_kernel<<<dim3(e->n_nbt, (unsigned)B), NB_T, 0, stream>>>(fpart, e->d_red_off, e->d_red_list, e->n_pairs, N,
@@ -1335,7 +1345,9 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
             ++launches;
         }
     }
-    if (energies) {
+    if (finalize_on_side) {
+        CK(cudaStreamWaitEvent(stream, e->ev_join, 0));
+    } else if (energies) {
         finalize_kernel<<<(unsigned)B, 128, 0, stream>>>(e_bonded, e->n_tiles, e_nb, e->n_pairs, energies, term_mask);
         ++launches;
     }
