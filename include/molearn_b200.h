@@ -157,7 +157,7 @@ int mlp_energy_last_launches(const mlp_energy* e);
 /* Optional per-kernel timing for benchmarks.  While enabled, mlp_energy_eval brackets each of
  * its kernels with CUDA events on the launching stream.  mlp_energy_profile_read waits for the
  * recorded events, returns the summed milliseconds and launch counts per kernel
- * (0 = nb pack, 1 = bonded, 2 = non-bonded pair kernel, 3 = non-bonded force reduction) and resets the totals. */
+ * (0 = unused, 1 = bonded, 2 = non-bonded pair kernel, 3 = non-bonded force reduction) and resets the totals. */
 int mlp_energy_profile(mlp_energy* e, int enable);
 int mlp_energy_profile_read(mlp_energy* e, double ms[4], int64_t counts[4]);
 

@@ -46,6 +46,7 @@
 // ------------------------------------------------------------------------------------------
 constexpr int BT = 256;          // bonded: threads per CTA
 constexpr int RB = 2, RA = 2, RT = 2;  // bonded: max bonds / angles / torsions per thread
+constexpr int SLOT_STRIDE = BT + 1;  // odd stride (in float4s): an atom's consecutive slots fall into different banks
 constexpr int PF = 4;            // bonded: coordinate elements staged per thread (3*(own+halo) <= PF*BT)
 constexpr int NF = 4;            // torsion Fourier orders kept (ff14SB periods are 1..4)
 constexpr int NB_T = 128;        // non-bonded tile edge (atoms)
@@ -269,7 +270,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
               float* __restrict__ grad, long sgb, long sgc, long sgn,
               const float* __restrict__ weights, float* __restrict__ e_part /* [B][n_tiles][3] or null */,
               int B, int conf_per_cta, uint32_t term_mask, int accumulate, int max_atoms, int max_cnt) {
-    constexpr int STRIDE = BT;         // slot (atom a, k-th contribution) at k*STRIDE + a
+    constexpr int STRIDE = SLOT_STRIDE;  // slot (atom a, k-th contribution) at k*STRIDE + a
     extern __shared__ float4 smem[];
     float4* sc = smem;                 // [max_atoms] coordinates of own + halo atoms
     float4* slots = smem + max_atoms;  // [max_cnt*STRIDE + 1] gradient slots; last = dump
@@ -943,7 +944,7 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
     int max_cnt = 1;
     for (int a = 0; a < N; ++a) max_cnt = std::max(max_cnt, (int)inc[a].size());
     max_cnt = (max_cnt + 3) & ~3;   // the gather reads whole groups of 4 slots
-    const int stride = BT;  // the kernel's compile-time slot stride
+    const int stride = SLOT_STRIDE;  // the kernel's compile-time slot stride
     if ((size_t)max_cnt * stride + 1 >= 0xffff) return 1;
     const uint32_t dump = (uint32_t)(max_cnt * stride);
 

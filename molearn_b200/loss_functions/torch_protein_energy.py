@@ -55,12 +55,12 @@ class _DeviceEnergy:
         _lib.check(_lib.lib().mlp_energy_profile(self._h, int(enable)))
 
     def profile_read(self):
-        """{'nb_pack'|'bonded'|'nb': (total ms, launches)} since the last read (waits for the events)."""
+        """{'bonded'|'nb'|'nb_reduce': (total ms, launches)} since the last read (waits for the events)."""
         import numpy as np
         ms, n = np.zeros(4, np.float64), np.zeros(4, np.int64)
         _lib.check(_lib.lib().mlp_energy_profile_read(self._h, ms.ctypes.data_as(ctypes.c_void_p),
                                                       n.ctypes.data_as(ctypes.c_void_p)))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("nb_pack", "bonded", "nb", "nb_reduce"))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("unused", "bonded", "nb", "nb_reduce")) if k != "unused"}
 
     def info(self):
         import numpy as np
