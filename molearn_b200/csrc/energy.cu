@@ -58,6 +58,12 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #ifndef BONDED_MINB
 #define BONDED_MINB 2   // bonded CTAs per SM the register budget is sized for
 #endif
+#ifndef NB2_MINB
+#define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
+#endif
+#ifndef NB_PACKED
+#define NB_PACKED 1  // 1: nb_kernel2 (packed FFMA2 pair loop), 0: scalar nb_kernel
+#endif
 #ifndef NB_MINB
 #define NB_MINB 4    // resident warps per SM sub-partition the register budget is sized for (4 -> 128 registers)
 #endif
@@ -109,6 +115,7 @@ struct mlp_energy {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap = true;
+    bool packed = NB_PACKED != 0;   // non-bonded pair loop in packed FP32 (FFMA2)
     // optional per-kernel timing (mlp_energy_profile): events on the launching stream
     bool profile = false;
     std::vector<std::array<cudaEvent_t, 2>> pending[4];  // per kernel: (start, stop) pairs not read yet
@@ -651,6 +658,186 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
     }
 }
 
+// ---- packed-FP32 variant -------------------------------------------------------------------------------
+// Blackwell's FMA pipe executes fma/mul/add.f32x2 (SASS FFMA2/FMUL2/FADD2): two FP32 lanes per instruction at
+// the same flop rate, i.e. half the issue slots.  The scalar kernel above is issue-bound (79 % issue, 63 % FMA
+// pipe), so here every FMA-pipe operation of the pair term is packed over two j-atoms: j data sit in shared
+// memory component-wise (x[128], y[128], ...), a lane reads float4s = two (j, j+1) pairs per component; the
+// lane's i-atoms are kept duplicated (v, v) in registers; i-force accumulators are (even-j, odd-j) partial
+// sums folded at the end of the item.  Same arithmetic per pair as nb_pair_fast (bit-identical results).
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
+
+template <bool GRAD, bool MASKED, bool FULL>
+__device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const float2 (&hRi)[NB_NI], const float2 (&sei)[NB_NI],
+                                           const float4 (&cj)[6], uint32_t m16,
+                                           float2 (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
+    float rmin = 3.0e38f;
+    const float2 neg1 = dup(-1.f), one = dup(1.f);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const float2 xj = p ? f2(cj[0].z, cj[0].w) : f2(cj[0].x, cj[0].y);
+        const float2 yj = p ? f2(cj[1].z, cj[1].w) : f2(cj[1].x, cj[1].y);
+        const float2 zj = p ? f2(cj[2].z, cj[2].w) : f2(cj[2].x, cj[2].y);
+        const float2 qj = p ? f2(cj[3].z, cj[3].w) : f2(cj[3].x, cj[3].y);
+        const float2 hj = p ? f2(cj[4].z, cj[4].w) : f2(cj[4].x, cj[4].y);
+        const float2 sj = p ? f2(cj[5].z, cj[5].w) : f2(cj[5].x, cj[5].y);
+#pragma unroll
+        for (int a = 0; a < NB_NI; ++a) {
+            float2 dx = __ffma2_rn(xj, neg1, xi[a][0]), dy = __ffma2_rn(yj, neg1, xi[a][1]), dz = __ffma2_rn(zj, neg1, xi[a][2]);
+            float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            float2 e12 = __fmul2_rn(sei[a], sj);
+            float2 qq = __fmul2_rn(xi[a][3], qj);
+            float2 Rij = __ffma2_rn(hRi[a], one, hj);          // add.f32x2 is lowered to two FADDs; FFMA2 by one stays packed
+            if (MASKED) {
+                const bool on0 = (m16 >> (4 * a + 2 * p)) & 1u, on1 = (m16 >> (4 * a + 2 * p + 1)) & 1u;
+                r2.x = on0 ? r2.x : NB_MASKED_R2; r2.y = on1 ? r2.y : NB_MASKED_R2;
+                e12.x = on0 ? e12.x : 0.f; e12.y = on1 ? e12.y : 0.f;
+                qq.x = on0 ? qq.x : 0.f; qq.y = on1 ? qq.y : 0.f;
+            }
+            rmin = fmin3(rmin, r2.x, r2.y);
+            float2 inv = f2(rsqrt_fast(fmaxf(r2.x, NB_THR2)), rsqrt_fast(fmaxf(r2.y, NB_THR2)));
+            float2 t = __fmul2_rn(Rij, inv);
+            float2 t2 = __fmul2_rn(t, t);
+            float2 t6 = __fmul2_rn(__fmul2_rn(t2, t2), t2);
+            float2 u6 = __fmul2_rn(e12, t6);
+            float2 ec = __fmul2_rn(qq, inv);
+            float2 u;
+            if (FULL) {
+                u = __ffma2_rn(u6, __ffma2_rn(t6, one, neg1), ec);
+                Sl = __ffma2_rn(u6, __ffma2_rn(t6, one, dup(-2.f)), Sl);
+            } else {
+                u = __ffma2_rn(u6, t6, ec);
+                Sl = __ffma2_rn(u6, t6, Sl);
+            }
+            Sc = __ffma2_rn(qq, inv, Sc);
+            if (GRAD) {
+                float2 s = __fmul2_rn(u, __fmul2_rn(inv, inv));
+                Fi[a][0] = __ffma2_rn(s, dx, Fi[a][0]); Fi[a][1] = __ffma2_rn(s, dy, Fi[a][1]); Fi[a][2] = __ffma2_rn(s, dz, Fi[a][2]);
+                Fj[p][0] = __ffma2_rn(s, dx, Fj[p][0]); Fj[p][1] = __ffma2_rn(s, dy, Fj[p][1]); Fj[p][2] = __ffma2_rn(s, dz, Fj[p][2]);
+            }
+        }
+    }
+    return !(rmin >= NB_THR2);
+}
+
+template <bool GRAD, bool FULL>
+__global__ void __launch_bounds__(32, 4 * NB2_MINB)
+nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const float* __restrict__ q, int N,
+           const float2* __restrict__ par, const int4* __restrict__ pairs,
+           const uint32_t* __restrict__ masks, int n_pairs, int B,
+           float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
+    __shared__ float4 s_j[6][32];                 // component c of the 128 j-atoms: s_j[c][g] = atoms 4g..4g+3
+    __shared__ uint32_t s_m[NB_T * 4];            // uint16 [g][lane] pair masks, as words
+    const int lane = threadIdx.x;
+    const long work = blockIdx.x;
+    const int p = (int)(work / B), b = (int)(work - (long)p * B);
+    if (weights && !e_part && weights[4 * b + 3] == 0.f) return;
+    const int4 IJ = pairs[p];
+    const long item = (long)b * n_pairs + p;
+    const int i0 = IJ.x * NB_T, j0 = IJ.y * NB_T;
+    const float* xb = x + (long)b * sxb;
+    const bool masked = IJ.z >= 0;
+
+    float2 xi[NB_NI][4], hRi[NB_NI], sei[NB_NI], Fi[NB_NI][3];
+#pragma unroll
+    for (int a = 0; a < NB_NI; ++a) {
+        const float4 v = nb_load_atom(xb, sxc, sxn, q, i0 + 4 * lane + a, N);
+        const float2 pr = par[i0 + 4 * lane + a];
+        xi[a][0] = dup(v.x); xi[a][1] = dup(v.y); xi[a][2] = dup(v.z); xi[a][3] = dup(v.w);
+        hRi[a] = dup(pr.x); sei[a] = dup(pr.y);
+        Fi[a][0] = Fi[a][1] = Fi[a][2] = dup(0.f);
+    }
+    {
+        float* sf = reinterpret_cast<float*>(s_j);
+#pragma unroll
+        for (int k = 0; k < NB_T / 32; ++k) {
+            const int jj = lane + 32 * k;
+            const float4 v = nb_load_atom(xb, sxc, sxn, q, j0 + jj, N);
+            const float2 pr = par[j0 + jj];
+            sf[0 * NB_T + jj] = v.x; sf[1 * NB_T + jj] = v.y; sf[2 * NB_T + jj] = v.z; sf[3 * NB_T + jj] = v.w;
+            sf[4 * NB_T + jj] = pr.x; sf[5 * NB_T + jj] = pr.y;
+        }
+    }
+    if (masked) {
+        const uint4* src = reinterpret_cast<const uint4*>(masks + (long)IJ.z * (NB_T * 4));
+        uint4* dst = reinterpret_cast<uint4*>(s_m);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = src[lane + 32 * k];
+    }
+    __syncwarp();
+
+    float2 Sl = dup(0.f), Sc = dup(0.f);
+    float2 Fj[2][3];
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) Fj[pp][0] = Fj[pp][1] = Fj[pp][2] = dup(0.f);
+    const int src_lane = (lane + 1) & 31;
+    const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m);
+    const int n_steps = IJ.w;
+#pragma unroll 1
+    for (int r = 0; r < n_steps; ++r) {
+        const int g = (lane + r) & 31;
+        float4 cj[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) cj[c] = s_j[c][g];
+        const uint32_t m16 = masked ? sm16[g * 32 + lane] : 0xffffu;
+        const bool close = masked ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
+                                  : nb_micro2<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+        if (close) {
+            // rare: exact correction through the scalar path (un-packed views of the same data)
+            float4 ui[NB_NI], uj[4];
+            float2 upi[NB_NI], upj[4];
+            float3 dFi[NB_NI], dFj[4];
+            float dSl = 0.f, dSc = 0.f;
+#pragma unroll
+            for (int a = 0; a < NB_NI; ++a) {
+                ui[a] = make_float4(xi[a][0].x, xi[a][1].x, xi[a][2].x, xi[a][3].x);
+                upi[a] = make_float2(hRi[a].x, sei[a].x);
+                dFi[a] = make_float3(0.f, 0.f, 0.f);
+            }
+            const float* cf = reinterpret_cast<const float*>(cj);
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                uj[bb] = make_float4(cf[0 * 4 + bb], cf[1 * 4 + bb], cf[2 * 4 + bb], cf[3 * 4 + bb]);
+                upj[bb] = make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
+                dFj[bb] = make_float3(0.f, 0.f, 0.f);
+            }
+            if (masked) nb_micro_fix<true, FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+            else nb_micro_fix<false, FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+#pragma unroll
+            for (int a = 0; a < NB_NI; ++a) { Fi[a][0].x += dFi[a].x; Fi[a][1].x += dFi[a].y; Fi[a][2].x += dFi[a].z; }
+            Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
+            Fj[0][0].y += dFj[1].x; Fj[0][1].y += dFj[1].y; Fj[0][2].y += dFj[1].z;
+            Fj[1][0].x += dFj[2].x; Fj[1][1].x += dFj[2].y; Fj[1][2].x += dFj[2].z;
+            Fj[1][0].y += dFj[3].x; Fj[1][1].y += dFj[3].y; Fj[1][2].y += dFj[3].z;
+            Sl.x += dSl; Sc.x += dSc;
+        }
+        if (GRAD) {
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    Fj[pp][c].x = __shfl_sync(0xffffffffu, Fj[pp][c].x, src_lane);
+                    Fj[pp][c].y = __shfl_sync(0xffffffffu, Fj[pp][c].y, src_lane);
+                }
+        }
+    }
+    if (GRAD) {
+        float* out = fpart + item * (6 * NB_T);
+        const int gl = (lane + n_steps) & 31;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            reinterpret_cast<float4*>(out + c * NB_T)[lane] =
+                make_float4(-(Fi[0][c].x + Fi[0][c].y), -(Fi[1][c].x + Fi[1][c].y), -(Fi[2][c].x + Fi[2][c].y), -(Fi[3][c].x + Fi[3][c].y));
+            reinterpret_cast<float4*>(out + (3 + c) * NB_T)[gl] = make_float4(Fj[0][c].x, Fj[0][c].y, Fj[1][c].x, Fj[1][c].y);
+        }
+    }
+    if (e_part) {
+        double e = (double)warp_sum(Sl.x + Sl.y) * (1.0 / 12.0) + (double)warp_sum(Sc.x + Sc.y);
+        if (lane == 0) e_part[item] = e;
+    }
+}
+
 // grad[b, n] (+)= w_nb[b] * (sum of the partial forces of every tile pair in n's tile row / column),
 // summed in list order: reproducible.
 __global__ void __launch_bounds__(NB_T)
@@ -1183,6 +1370,7 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
     if (rc == MLP_OK) rc = pack_nonbonded(E, *t);
     if (rc == MLP_OK) {
         if (const char* env = std::getenv("MLP_NO_OVERLAP")) E->overlap = std::atoi(env) == 0;
+        if (const char* env = std::getenv("MLP_NB_PACKED")) E->packed = std::atoi(env) != 0;
         if (cudaStreamCreateWithFlags(&E->side, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&E->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -1323,8 +1511,15 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         const bool full = e->nb_mode == MLP_NB_FULL;
         double* ep = energies ? e_nb : nullptr;
 #define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
-        if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
-        else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
+#define NB_LAUNCH2(G, F) nb_kernel2<G, F><<<(unsigned)items, 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
+        if (e->packed) {
+            if (grad) { if (full) NB_LAUNCH2(true, true); else NB_LAUNCH2(true, false); }
+            else { if (full) NB_LAUNCH2(false, true); else NB_LAUNCH2(false, false); }
+        } else {
+            if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
+            else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
+        }
+#undef NB_LAUNCH2
 #undef NB_LAUNCH
         prof_end(2);
         ++launches;
