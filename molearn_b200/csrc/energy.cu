@@ -61,6 +61,9 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #ifndef NB2_MINB
 #define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
 #endif
+#ifndef NB2_RCP
+#define NB2_RCP 0
+#endif
 #ifndef NB_PACKED
 #define NB_PACKED 1  // 1: nb_kernel2 (packed FFMA2 pair loop), 0: scalar nb_kernel
 #endif
@@ -696,7 +699,8 @@ __device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const fl
                 qq.x = on0 ? qq.x : 0.f; qq.y = on1 ? qq.y : 0.f;
             }
             rmin = fmin3(rmin, r2.x, r2.y);
-            float2 inv = f2(rsqrt_fast(fmaxf(r2.x, NB_THR2)), rsqrt_fast(fmaxf(r2.y, NB_THR2)));
+            const float2 r2c = f2(fmaxf(r2.x, NB_THR2), fmaxf(r2.y, NB_THR2));
+            float2 inv = f2(rsqrt_fast(r2c.x), rsqrt_fast(r2c.y));
             float2 t = __fmul2_rn(Rij, inv);
             float2 t2 = __fmul2_rn(t, t);
             float2 t6 = __fmul2_rn(__fmul2_rn(t2, t2), t2);
@@ -712,7 +716,11 @@ __device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const fl
             }
             Sc = __ffma2_rn(qq, inv, Sc);
             if (GRAD) {
+#if NB2_RCP
+                float2 s = __fmul2_rn(u, f2(rcp_fast(r2c.x), rcp_fast(r2c.y)));   // 1/r^2 on the (idle) MUFU pipe
+#else
                 float2 s = __fmul2_rn(u, __fmul2_rn(inv, inv));
+#endif
                 Fi[a][0] = __ffma2_rn(s, dx, Fi[a][0]); Fi[a][1] = __ffma2_rn(s, dy, Fi[a][1]); Fi[a][2] = __ffma2_rn(s, dz, Fi[a][2]);
                 Fj[p][0] = __ffma2_rn(s, dx, Fj[p][0]); Fj[p][1] = __ffma2_rn(s, dy, Fj[p][1]); Fj[p][2] = __ffma2_rn(s, dz, Fj[p][2]);
             }
