@@ -115,6 +115,10 @@ class _EnergyFunction(torch.autograd.Function):
         if saved is None:
             raise RuntimeError("TorchProteinEnergy: backward through a forward that did not record a gradient")
         terms = [t for t in range(4) if ctx.term_mask >> t & 1]
+        if gout.stride() == (0, 0):
+            # upstream is one scalar broadcast over [B,4] (e.g. ``E.sum().backward()``): every term of every
+            # conformation has the same weight, so the saved unit-weight gradient only needs scaling
+            return saved * gout.reshape(-1)[0].to(saved.dtype), None, None
         gout = gout.contiguous().float()
         t0 = terms[0]
         # dL/dx = sum_t gout[b,t] dE_t/dx = gout[b,t0] * (saved = sum_t dE_t/dx) + sum_{t>t0} (gout[b,t]-gout[b,t0]) dE_t/dx
