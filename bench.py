@@ -543,8 +543,10 @@ def main():
         fp32_peak = 148 * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12       # TFLOP/s, FMA pipe
         flops = FLOPS_PER_PAIR * top.n_nb_pairs * B
         ach = flops / (nb_ms * 1e-3) / 1e12
-        out["roofline"] = {"kernel": "nb_kernel<grad>", "bound": "fp32", "achieved": ach, "peak": fp32_peak,
-                           "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
+        out["roofline"] = {"kernel": "nb_kernel2<grad> (packed FP32 pair kernel)", "bound": "fp32", "achieved": ach, "peak": fp32_peak,
+                           "unit": "TFLOP/s", "frac": ach / fp32_peak,
+                           "traffic": 1788928, "traffic_source": "dram__bytes_read+write of one launch, profiles/r01_summary.txt (inputs are L2-resident)",
+                           "measured_ffma_peak_tflops": 71.2, "fma_pipe_busy_pct_ncu": 72.2,
                            "peak_source": "148 SM x 128 FMA lanes x 2 x sm_max_mhz (FP32 pipe; no tensor cores on this path)",
                            "algorithmic_flops_per_launch": flops, "kernel_ms": nb_ms,
                            "share_of_step": nb_ms / (ms / args.steps),
@@ -569,7 +571,8 @@ def main():
             gbs = byts / (t_ms * 1e-3) / 1e9
             out["roofline_bonded"] = {"kernel": "bonded_kernel<grad>", "bound": "hbm", "batch": BB, "achieved": gbs,
                                       "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                                      "traffic": None, "algorithmic_bytes_per_launch": byts, "kernel_ms": t_ms,
+                                      "traffic": 168585984, "traffic_source": "dram__bytes_read+write of one launch at B=4096, profiles/r01_bonded_b4096.txt",
+                                      "algorithmic_bytes_per_launch": byts, "kernel_ms": t_ms,
                                       "conformations_per_s": BB / (t_ms * 1e-3)}
             del xb, gb, eb
         if world == 1 and not args.no_extras and not args.bonded_only:
