@@ -15,7 +15,8 @@ Files
                             fp32 reference batch values, fp64 per-conformation energies and
                             fp64 gradients
 Cases: bbcb (N,CA,CB,C,O -> 2145 atoms), heavy (all 3286), tile2 (two bbcb tiles as two
-chains, SURVEY 8d config 4 construction, 4288 -> 4286 atoms).
+chains, SURVEY 8d config 4 construction, 4288 -> 4286 atoms), pep28 (one residue of each of the 28
+amino12.lib templates with all hydrogens, 444 atoms, random-walk coordinates).
 """
 from __future__ import annotations
 
@@ -29,7 +30,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
-from oracle import ref_loader  # noqa: E402
+from oracle import ref_loader, topology_oracle  # noqa: E402
 from molearn_b200.data.pdb_reader import read_pdb_frames, select_atoms  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -161,6 +162,21 @@ def main():
     xh = np.concatenate([X[:2], X[2:4] + 0.5 * noise])
     obj, _, _ = ref_loader.build_reference(torch.from_numpy(X[0].T.copy()), info)
     energy_case("heavy", obj, xh, grad_frames=[0, 2])
+
+    # --- every residue template of amino12.lib, all atoms incl. hydrogens ------------------
+    # 28 residues (ALA ... VAL incl. ASH/CYM/CYX/GLH/HID/HIE/HIP/HYP/LYN), template atom order, consecutive
+    # resids; coordinates are a seeded random walk (0.9 A steps): not a structure, but finite, and it
+    # exercises every atom type / bond / angle / torsion parameter the templates can produce, rings,
+    # hydrogens, and the close-contact branch of the non-bonded term.
+    at, _, _, _ = topology_oracle.parse_forcefield(ref_loader.PARAM_DIR)
+    pinfo = np.array([(name, res, k + 1) for k, res in enumerate(at) for name in at[res]], dtype=object)
+    rng = np.random.default_rng(28)
+    walk = np.cumsum(rng.normal(scale=0.9, size=(len(pinfo), 3)), axis=0).astype(np.float32)
+    xp = np.stack([walk, walk * 1.5, walk + rng.normal(scale=0.3, size=walk.shape).astype(np.float32),
+                   walk * 0.6]).astype(np.float32)
+    obj = topology_case("pep28", pinfo, xp[0])
+    obj, _, _ = ref_loader.build_reference(torch.from_numpy(xp[0].T.copy()), pinfo)
+    energy_case("pep28", obj, xp, grad_frames=[0, 1, 3])
 
     # --- two tiles = two chains -----------------------------------------------------------
     tinfo, tx = make_tiles(binfo, bX, 2, lambda t: t % 16)

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ("bbcb", "heavy", "tile2")
+CASES = ("bbcb", "heavy", "tile2", "pep28")
 
 
 def pytest_configure(config):

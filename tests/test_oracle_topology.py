@@ -30,4 +30,10 @@ def test_nb_pair_parameters(case, golden_topo, param_dir):
     nz = g["nb_A"] != 0
     assert np.max(np.abs(A[nz] / g["nb_A"][nz] - 1)) < 5e-6        # reference A carries fp32 cdist noise
     n = len(g["in_names"])
-    assert int(g["nb_nnz_A"]) == n * (n - 1) // 2 - len(to.exclusion_pairs(t))
+    # non-zero A entries = non-excluded pairs whose two atoms both have a well depth (hydroxyl H has eps = 0)
+    ex = to.exclusion_pairs(t)
+    live = g["atom_e"] > 0
+    n_live = int(live.sum())
+    expect = n_live * (n_live - 1) // 2 - int((live[ex[:, 0]] & live[ex[:, 1]]).sum())
+    assert int(g["nb_nnz_A"]) == expect
+    assert int(g["nb_nnz_q"]) == n * (n - 1) // 2 - len(ex)             # no template atom has zero charge

@@ -40,7 +40,7 @@ def test_builder_bit_exact(case, golden_topo, param_dir):
     assert np.array_equal(t.atom_R, g["atom_R"]) and np.array_equal(t.atom_e, g["atom_e"])
     assert np.array_equal(t.atom_charges.astype(np.float32), g["atom_charges"].astype(np.float32))
     n = t.n_atoms
-    assert t.n_nb_pairs == int(g["nb_nnz_A"]) == n * (n - 1) // 2 - len(t.exclusions)
+    assert t.n_nb_pairs == int(g["nb_nnz_q"]) == n * (n - 1) // 2 - len(t.exclusions)
     ex = t.exclusions
     assert np.all(ex[:, 0] < ex[:, 1]) and len(np.unique(ex, axis=0)) == len(ex)
 
