@@ -143,6 +143,11 @@ int mlp_energy_info(const mlp_energy* e, int64_t info[8]);
  *   workspace  dev, >= mlp_energy_workspace_bytes(e,B,term_mask,grad!=NULL) bytes, 16-byte aligned
  *   stream     cudaStream_t
  * Non-finite coordinates are not an error: they propagate into that conformation's outputs.
+ *
+ * Concurrency: work is ordered on `stream`; when both bonded and non-bonded terms are requested the bonded
+ * kernel runs on a private stream of the handle that forks from and joins back into `stream` (so the call is
+ * still stream-ordered for the caller and capturable into a CUDA graph).  One handle serves one host thread at
+ * a time; use one handle per device and per concurrently calling thread.
  */
 int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B,
                     int64_t sxb, int64_t sxc, int64_t sxn,
