@@ -34,11 +34,22 @@ class _DeviceEnergy:
         _lib.check(_lib.lib().mlp_energy_create(topology.handle, idx, nb_mode, ctypes.byref(self._h)))
         self.launches = 0  # kernels launched through this handle (bench.py reports it)
 
+    # scratch memory per call is capped: larger batches are evaluated in chunks of conformations
+    MAX_WORKSPACE_BYTES = int(float(__import__("os").environ.get("MLP_MAX_WORKSPACE_GB", "8")) * 2 ** 30)
+
     def eval(self, x, energies, grad, weights, term_mask, accumulate=False):
         """x: [B,3,N] logical fp32 CUDA tensor (any strides). energies [B,4] or None; grad like x or None."""
         L = _lib.lib()
         B = x.shape[0]
         nbytes = L.mlp_energy_workspace_bytes(self._h, B, term_mask, int(grad is not None))
+        if nbytes > self.MAX_WORKSPACE_BYTES and B > 1:
+            per = max(1, (nbytes - 512) // B)
+            chunk = max(1, int(self.MAX_WORKSPACE_BYTES // per))
+            for lo in range(0, B, chunk):
+                sl = slice(lo, min(B, lo + chunk))
+                self.eval(x[sl], None if energies is None else energies[sl], None if grad is None else grad[sl],
+                          None if weights is None else weights[sl], term_mask, accumulate)
+            return
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         gs = (grad.stride(0), grad.stride(1), grad.stride(2)) if grad is not None else (0, 0, 0)
         stream = torch.cuda.current_stream(x.device).cuda_stream

@@ -236,3 +236,14 @@ def test_general_torsion_phase_kernel(dev, golden_topo, golden_energy, monkeypat
     for q, f in enumerate(gf):
         assert abs(float(e[q, 2]) - en["e64"][f, 2]) < TOL * en["e64"][f, 2]
         assert rel(got[q], en["g64"][q, 2]) < TOL
+
+
+def test_chunked_evaluation_matches(dev, energy_objs, golden_energy, monkeypatch):
+    """Batches whose scratch memory exceeds the cap are evaluated in chunks: same bits as one call."""
+    from molearn_b200.loss_functions import torch_protein_energy as tp
+    tpe = energy_objs("bbcb")
+    x = torch.from_numpy(golden_energy("bbcb")["x"]).to(dev).permute(0, 2, 1)
+    e1, g1 = tpe.energy_and_gradient(x)
+    monkeypatch.setattr(tp._DeviceEnergy, "MAX_WORKSPACE_BYTES", 3 * 2 ** 20)   # forces chunks of a few conformations
+    e2, g2 = tpe.energy_and_gradient(x)
+    assert torch.equal(e1, e2) and torch.equal(g1, g2)
