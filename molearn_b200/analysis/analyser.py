@@ -352,6 +352,81 @@ class MolearnAnalysis:
             out["dataset_inversions"] = count(ds)
         return out
 
+    # -- backbone angles / dihedrals of a dataset and its reconstruction (analyser.py:475-566; host-side NumPy:
+    #    these feed plots, not scans) ---------------------------------------------------------------------------
+    def _residue_indices(self):
+        """Per residue (first appearance order) the first index of N / CA / C / O / CB, -1 where absent."""
+        info = self._atominfo
+        order, first = [], {}
+        for i, (a, _, r) in enumerate(info):
+            r = int(r)
+            if r not in first:
+                first[r] = {}
+                order.append(r)
+            first[r].setdefault(str(a), i)
+        return {k: np.array([first[r].get(k, -1) for r in order]) for k in ("N", "CA", "C", "O", "CB")}
+
+    @staticmethod
+    def _angles(p0, p1, p2):
+        """analyser.py:791-805."""
+        b0, b1 = p0 - p1, p2 - p1
+        b0 = b0 / np.linalg.norm(b0, axis=-1, keepdims=True)
+        b1 = b1 / np.linalg.norm(b1, axis=-1, keepdims=True)
+        return np.arccos(np.einsum("...i,...i->...", b0, b1))
+
+    @staticmethod
+    def _dihedrals(p0, p1, p2, p3):
+        """Dihedral angle p0-p1-p2-p3 in radians.  analyser.py:808-828 multiplies two sums where the standard
+        formula sums a product (``y = sum(cross(b1, v) * w)``); the standard formula is used here."""
+        b0, b1, b2 = p0 - p1, p2 - p1, p3 - p2
+        b1 = b1 / np.linalg.norm(b1, axis=-1, keepdims=True)
+        v = b0 - np.sum(b0 * b1, axis=-1, keepdims=True) * b1
+        w = b2 - np.sum(b2 * b1, axis=-1, keepdims=True) * b1
+        return np.arctan2(np.sum(np.cross(b1, v) * w, axis=-1), np.sum(v * w, axis=-1))
+
+    def _get_dihedrals(self, data):
+        idx = self._residue_indices()
+        d = data.numpy() if torch.is_tensor(data) else np.asarray(data)
+        N, CA, C = d[:, idx["N"]], d[:, idx["CA"]], d[:, idx["C"]]
+        out = {"Phi": self._dihedrals(C[:, :-1], N[:, 1:], CA[:, 1:], C[:, 1:]),
+               "Psi": self._dihedrals(N[:, :-1], CA[:, :-1], C[:, :-1], N[:, 1:]),
+               "Omega": self._dihedrals(CA[:, :-1], C[:, :-1], N[:, 1:], CA[:, 1:])}
+        valid = idx["CB"] >= 0
+        if valid.any():
+            out["Improper Torsion"] = self._dihedrals(N[:, valid], CA[:, valid], C[:, valid], d[:, idx["CB"][valid]])
+        return out
+
+    def _get_angles(self, data):
+        idx = self._residue_indices()
+        d = data.numpy() if torch.is_tensor(data) else np.asarray(data)
+        N, CA, C = d[:, idx["N"]], d[:, idx["CA"]], d[:, idx["C"]]
+        out = {"N-CA-C": self._angles(N, CA, C), "CA-C-N": self._angles(CA[:, :-1], C[:, :-1], N[:, 1:]),
+               "C-N-CA": self._angles(C[:, :-1], N[:, 1:], CA[:, 1:])}
+        if (idx["O"] >= 0).all():
+            O = d[:, idx["O"]]
+            out["CA-C-O"] = self._angles(CA, C, O)
+            out["O-C-N"] = self._angles(O[:, :-1], C[:, :-1], N[:, 1:])
+        valid = idx["CB"] >= 0
+        if valid.any():
+            CB = d[:, idx["CB"][valid]]
+            out["N-CA-CB"] = self._angles(N[:, valid], CA[:, valid], CB)
+            out["CA-CB-C"] = self._angles(CA[:, valid], CB, C[:, valid])
+        return out
+
+    def get_dihedrals(self, key):
+        ds, dec = self._structures(key)
+        out = dict(decoded_dihedrals=self._get_dihedrals(dec))
+        if ds is not None:
+            out["dataset_dihedrals"] = self._get_dihedrals(ds)
+        return out
+
+    def get_angles(self, key):
+        ds, dec = self._structures(key)
+        out = dict(decoded_angles=self._get_angles(dec))
+        if ds is not None:
+            out["dataset_angles"] = self._get_angles(ds)
+        return out
+
     def _scan_geometry(self):
         if "_geometry_rows" not in self.__dict__ or self._geometry_rows_grid is not self._encoded.get("grid"):
             geom = self._geometry()

@@ -127,3 +127,19 @@ def test_two_rank_scan_equals_single_rank(tmp_path):
     rmsd, drift, _, _ = ma.scan_error()
     got = np.load(out)
     assert np.array_equal(got[0], rmsd) and np.array_equal(got[1], drift)
+
+
+def test_backbone_angles_and_dihedrals_on_md_frames():
+    """get_angles / get_dihedrals on real MurD frames: textbook backbone geometry (omega ~ 180 deg, N-CA-C ~ 111 deg)."""
+    from conftest import load_golden
+    g = load_golden("murd_input")
+    keep = np.isin(g["names"], ("N", "CA", "CB", "C", "O"))
+    ma = MolearnAnalysis()
+    ma._atominfo = np.array(list(zip(g["names"][keep], g["resnames"][keep], g["resids"][keep])), dtype=object)
+    x = g["coords"][:2, keep]
+    dih = ma._get_dihedrals(x)
+    ang = ma._get_angles(x)
+    assert dih["Phi"].shape == (2, 436) and dih["Improper Torsion"].shape == (2, 397)      # 437 residues, 40 GLY
+    assert np.median(np.abs(np.degrees(dih["Omega"]))) > 170                                # trans peptide bonds
+    assert abs(np.degrees(ang["N-CA-C"]).mean() - 111) < 3 and abs(np.degrees(ang["CA-C-O"]).mean() - 120.5) < 3
+    assert np.all(np.degrees(dih["Improper Torsion"]) > 0) or np.all(np.degrees(dih["Improper Torsion"]) < 0)   # one chirality
