@@ -247,3 +247,35 @@ def test_chunked_evaluation_matches(dev, energy_objs, golden_energy, monkeypatch
     monkeypatch.setattr(tp._DeviceEnergy, "MAX_WORKSPACE_BYTES", 3 * 2 ** 20)   # forces chunks of a few conformations
     e2, g2 = tpe.energy_and_gradient(x)
     assert torch.equal(e1, e2) and torch.equal(g1, g2)
+
+
+def test_tiny_systems_vs_oracle(dev, param_dir):
+    """One residue (4 atoms, no torsion), a dipeptide, and a 3-residue peptide with all hydrogens: single tiles,
+    inert padding records, mostly-masked non-bonded tile."""
+    from molearn_b200 import TorchProteinEnergy
+    from oracle import topology_oracle as to
+    rng = np.random.default_rng(2)
+    at, _, _, _ = to.parse_forcefield(param_dir)
+    systems = {
+        "gly": [("N", "GLY", 1), ("CA", "GLY", 1), ("C", "GLY", 1), ("O", "GLY", 1)],
+        "ala_ser": [(a, "ALA", 1) for a in ("N", "CA", "CB", "C", "O")] + [(a, "SER", 2) for a in ("N", "CA", "CB", "OG", "C", "O")],
+        "full_h": [(a, r, k + 1) for k, r in enumerate(("ALA", "TRP", "PRO")) for a in at[r]],
+    }
+    for name, atoms in systems.items():
+        info = np.array(atoms, dtype=object)
+        n = len(info)
+        topo = to.build_topology(param_dir, list(info[:, 0]), list(info[:, 1]), [int(r) for r in info[:, 2]])
+        xs = (np.cumsum(rng.normal(scale=1.2, size=(3, n, 3)), axis=1)).astype(np.float32)
+        tpe = TorchProteinEnergy(None, info, device=dev)
+        x = torch.from_numpy(xs).to(dev).permute(0, 2, 1)
+        e = tpe.energy_per_conformation(x).double().cpu().numpy()
+        g = per_term_grads(tpe, x)
+        for q in range(3):
+            we, wg = eo.energy_all(xs[q], topo)
+            for k, term in enumerate(TERMS):
+                if abs(we[k]) > 0:
+                    assert abs(e[q, k] - we[k]) < TOL * abs(we[k]), (name, term, q, e[q, k], we[k])
+                else:
+                    assert e[q, k] == 0.0, (name, term)
+                if np.linalg.norm(wg[k]) > 0:
+                    assert rel(g[k, q], wg[k]) < TOL, (name, term, q, rel(g[k, q], wg[k]))
