@@ -1232,6 +1232,27 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
         }
         bt.n_tors = (int)tors_all.size() - bt.tors_off;
 
+        // self-check of the packed records (compute-sanitizer is not available on the target pool): every local
+        // atom index addresses a staged atom, every slot id addresses an allocated slot or the dump slot
+        {
+            bool ok = true;
+            auto at_ok = [&](uint32_t la) { return la < (uint32_t)n_at; };
+            auto sl_ok = [&](uint32_t sl) { return sl <= dump; };
+            for (size_t q = bt.bond_off; q < bonds_all.size(); ++q) {
+                const BondRec& r = bonds_all[q];
+                ok = ok && at_ok(r.ij & 0x7fffu) && at_ok(r.ij >> 16) && sl_ok(r.slots & 0xffffu) && sl_ok(r.slots >> 16);
+            }
+            for (size_t q = bt.angle_off; q < angles_all.size(); ++q) {
+                const AngleRec& r = angles_all[q];
+                ok = ok && at_ok(r.ij & 0x7fffu) && at_ok(r.ij >> 16) && at_ok(r.k) && sl_ok(r.s_ij & 0xffffu) && sl_ok(r.s_ij >> 16) && sl_ok(r.s_k);
+            }
+            for (size_t q = bt.tors_off; q < tors_all.size(); ++q) {
+                const TorsRec& r = tors_all[q];
+                ok = ok && at_ok(r.ij & 0x7fffu) && at_ok(r.ij >> 16) && at_ok(r.kl & 0xffffu) && at_ok(r.kl >> 16) &&
+                     sl_ok(r.s_ij & 0xffffu) && sl_ok(r.s_ij >> 16) && sl_ok(r.s_kl & 0xffffu) && sl_ok(r.s_kl >> 16);
+            }
+            if (!ok) { mlp_set_error("pack_bonded: internal error, record index out of range"); return MLP_E_ARG; }
+        }
         bt.halo_off = (int)halo_all.size(); bt.n_halo = (int)halo.size();
         halo_all.insert(halo_all.end(), halo.begin(), halo.end());
         max_atoms = std::max(max_atoms, n_at);
