@@ -58,9 +58,12 @@ def lib():
     if _LIB is None:
         path = library_path()
         if not os.path.exists(path):
-            raise ImportError(
-                f"{path} is missing: the molearn_b200 CUDA extension is not built and there is no CPU "
-                "fallback.  Run `python -m molearn_b200.build` (needs nvcc).")
+            try:                                   # a fresh checkout: compile once (nvcc, ~20 s); never a CPU path
+                _build.build_library()
+            except Exception as exc:
+                raise ImportError(
+                    f"{path} is missing and could not be built ({exc}): the molearn_b200 CUDA extension is required, "
+                    "there is no CPU fallback.  Run `python -m molearn_b200.build` (needs nvcc).") from exc
         L = ctypes.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError if the library does not export the symbol
