@@ -129,7 +129,7 @@ int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B, uint32_t term
  * pairs, masked NB tile pairs, padded atom count. */
 int mlp_energy_info(const mlp_energy* e, int64_t info[8]);
 
-/* Energies and (optionally) gradient of B conformations.
+/* Energies and (optionally) gradient of B <= 65535 conformations.
  *
  *   x          dev, logical shape [B,3,N] fp32 addressed as x[b*sxb + c*sxc + n*sxn]
  *              (the reference layout [B,3,N] contiguous is sxb=3N,sxc=N,sxn=1; a decoder output

@@ -1477,6 +1477,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
                     void* workspace, int64_t workspace_bytes, void* stream_) {
     if (!e || B < 0 || (term_mask & ~MLP_TERM_ALL)) { mlp_set_error("mlp_energy_eval: bad argument"); return MLP_E_ARG; }
     if (B == 0 || e->N == 0) { e->last_launches = 0; return MLP_OK; }  // empty batch: nothing to do (pointers may be null)
+    if (B > 65535) { mlp_set_error("mlp_energy_eval: at most 65535 conformations per call (split the batch)"); return MLP_E_ARG; }
     if (!x || !workspace) { mlp_set_error("mlp_energy_eval: null x / workspace"); return MLP_E_ARG; }
     const Workspace W = layout(e, B, term_mask, grad != nullptr);
     if (workspace_bytes < (int64_t)W.total) { mlp_set_error("mlp_energy_eval: workspace too small"); return MLP_E_WORKSPACE; }

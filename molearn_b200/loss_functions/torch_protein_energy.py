@@ -35,6 +35,7 @@ class _DeviceEnergy:
         self.launches = 0  # kernels launched through this handle (bench.py reports it)
 
     # scratch memory per call is capped: larger batches are evaluated in chunks of conformations
+    MAX_BATCH_PER_CALL = 32768      # grid.y of the per-conformation kernels is limited to 65535
     MAX_WORKSPACE_BYTES = int(float(__import__("os").environ.get("MLP_MAX_WORKSPACE_GB", "8")) * 2 ** 30)
 
     def eval(self, x, energies, grad, weights, term_mask, accumulate=False):
@@ -42,9 +43,9 @@ class _DeviceEnergy:
         L = _lib.lib()
         B = x.shape[0]
         nbytes = L.mlp_energy_workspace_bytes(self._h, B, term_mask, int(grad is not None))
-        if nbytes > self.MAX_WORKSPACE_BYTES and B > 1:
+        if (nbytes > self.MAX_WORKSPACE_BYTES or B > self.MAX_BATCH_PER_CALL) and B > 1:
             per = max(1, (nbytes - 512) // B)
-            chunk = max(1, int(self.MAX_WORKSPACE_BYTES // per))
+            chunk = max(1, min(self.MAX_BATCH_PER_CALL, int(self.MAX_WORKSPACE_BYTES // per)))
             for lo in range(0, B, chunk):
                 sl = slice(lo, min(B, lo + chunk))
                 self.eval(x[sl], None if energies is None else energies[sl], None if grad is None else grad[sl],
