@@ -33,6 +33,7 @@ class _DeviceEnergy:
         self.index = idx
         _lib.check(_lib.lib().mlp_energy_create(topology.handle, idx, nb_mode, ctypes.byref(self._h)))
         self.launches = 0  # kernels launched through this handle (bench.py reports it)
+        self._ws_bytes = {}
 
     # scratch memory per call is capped: larger batches are evaluated in chunks of conformations
     MAX_BATCH_PER_CALL = 32768      # grid.y of the per-conformation kernels is limited to 65535
@@ -42,7 +43,10 @@ class _DeviceEnergy:
         """x: [B,3,N] logical fp32 CUDA tensor (any strides). energies [B,4] or None; grad like x or None."""
         L = _lib.lib()
         B = x.shape[0]
-        nbytes = L.mlp_energy_workspace_bytes(self._h, B, term_mask, int(grad is not None))
+        key = (B, term_mask, grad is not None)
+        nbytes = self._ws_bytes.get(key)
+        if nbytes is None:
+            nbytes = self._ws_bytes[key] = L.mlp_energy_workspace_bytes(self._h, B, term_mask, int(grad is not None))
         if (nbytes > self.MAX_WORKSPACE_BYTES or B > self.MAX_BATCH_PER_CALL) and B > 1:
             per = max(1, (nbytes - 512) // B)
             chunk = max(1, min(self.MAX_BATCH_PER_CALL, int(self.MAX_WORKSPACE_BYTES // per)))
@@ -111,8 +115,11 @@ class _EnergyFunction(torch.autograd.Function):
         energies = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
         need_grad = ctx.needs_input_grad[0]
         grad = torch.empty_like(xd) if need_grad else None
-        with torch.cuda.device(x.device):
+        if torch.cuda.current_device() == dev.index:
             dev.eval(xd, energies, grad, None, term_mask)
+        else:
+            with torch.cuda.device(x.device):
+                dev.eval(xd, energies, grad, None, term_mask)
         ctx.dev, ctx.term_mask = dev, term_mask
         ctx.save_for_backward(xd, grad)
         ctx.set_materialize_grads(False)
@@ -221,8 +228,12 @@ class TorchProteinEnergy:
             energies = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
         if grad is None:
             grad = torch.empty_like(x)
-        with torch.cuda.device(x.device):
-            self._dev().eval(x, energies, grad, None, TERM_ALL if nonbonded else TERM_BONDED)
+        dev = self._dev()
+        if torch.cuda.current_device() == dev.index:
+            dev.eval(x, energies, grad, None, TERM_ALL if nonbonded else TERM_BONDED)
+        else:
+            with torch.cuda.device(x.device):
+                dev.eval(x, energies, grad, None, TERM_ALL if nonbonded else TERM_BONDED)
         return energies, grad
 
     # -- reference API ------------------------------------------------------------------------
