@@ -233,7 +233,7 @@ __device__ __forceinline__ void torsion_term(const float4* sc, float4* slots, co
     float3 F = f3(sc[i]) - rj, G = rj - rk, H = f3(sc[l]) - rk;
     float3 A = cross(F, G), B = cross(H, G);
     float G2 = dot(G, G);
-    float iG = rsqrt_nr(G2);
+    float iG = G2 > 0.f ? rsqrt_nr(G2) : (G2 == 0.f ? 0.f : G2);   // coincident j,k: |G| = 0, phi = atan2(0,0) = 0 like the reference
     float Gn = G2 * iG;
     float X = dot(A, B), Y = -Gn * dot(B, F);
     float rho2 = fmaf(X, X, Y * Y);

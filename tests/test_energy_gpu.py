@@ -279,3 +279,46 @@ def test_tiny_systems_vs_oracle(dev, param_dir):
                     assert e[q, k] == 0.0, (name, term)
                 if np.linalg.norm(wg[k]) > 0:
                     assert rel(g[k, q], wg[k]) < TOL, (name, term, q, rel(g[k, q], wg[k]))
+
+
+def test_ten_thousand_atoms_vs_oracle(dev, golden_topo):
+    """BASELINE config 4 system (5 chains, 10 715 atoms, 84 x 84 non-bonded tiles): energies and gradient of one
+    noisy conformation against the fp64 oracle."""
+    from molearn_b200 import TorchProteinEnergy
+    from molearn_b200.data import tile_system
+    g = load_golden_murd_bbcb()
+    tinfo, x = tile_system(g[0], g[1], 5, batch=1, noise=0.3, seed=5)
+    tpe = TorchProteinEnergy(None, tinfo, device=dev)
+    topo = tpe.topology.as_dict()
+    xd = torch.from_numpy(x).to(dev).permute(0, 2, 1).requires_grad_(True)
+    e = tpe.energy_per_conformation(xd)
+    e.sum().backward()
+    want_e, want_g = eo.energy_all(x[0], topo)
+    got = e.detach().double().cpu().numpy()[0]
+    for k, name in enumerate(TERMS):
+        assert abs(got[k] - want_e[k]) < TOL * abs(want_e[k]), (name, got[k], want_e[k])
+    assert rel(xd.grad.permute(0, 2, 1).double().cpu().numpy()[0], want_g.sum(0)) < TOL
+
+
+def load_golden_murd_bbcb():
+    from conftest import load_golden
+    g = load_golden("murd_input")
+    keep = np.isin(g["names"], ("N", "CA", "CB", "C", "O"))
+    info = atominfo_from({"in_names": g["names"][keep], "in_resnames": g["resnames"][keep], "in_resids": g["resids"][keep]})
+    return info, np.ascontiguousarray(g["coords"][:, keep])
+
+
+def test_coincident_atoms_follow_reference_semantics(dev, energy_objs, golden_topo, golden_energy):
+    """Two bonded atoms on the same point: the bond term is finite (K r0^2), every angle with that arm is 0/0 = NaN,
+    torsions around it are atan2(0,0) = 0 -> finite - the same per-term outcome as the reference's forward pass."""
+    topo = golden_topo("bbcb")
+    tpe = energy_objs("bbcb")
+    xs = golden_energy("bbcb")["x"][:2].copy()
+    i, j = (int(v) for v in topo["bond_idxs"][700])
+    xs[1, j] = xs[1, i]
+    e = tpe.energy_per_conformation(torch.from_numpy(xs).to(dev).permute(0, 2, 1)).double().cpu().numpy()
+    want, _ = eo.energy_all(xs[1], topo, want_grad=False)
+    assert np.isfinite(e[0]).all()
+    assert np.isnan(want[1]) and np.isnan(e[1, 1])                       # angle: NaN in both
+    for k in (0, 2, 3):                                                  # bond, torsion, nb: finite and equal
+        assert np.isfinite(want[k]) and abs(e[1, k] - want[k]) < TOL * abs(want[k]), (k, e[1, k], want[k])
