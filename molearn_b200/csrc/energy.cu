@@ -18,14 +18,16 @@
 //   evaluated by both tiles (energy counted by the owner of role 0).
 //
 // Non-bonded kernel
-//   Work item = (conformation, 128x128 atom tile pair J>=I), one warp each.  A lane owns NI=4
-//   i-atoms in registers for the whole tile; the 32 groups of 4 j-atoms rotate through the lanes
-//   together with their force accumulators (Newton's third law for 12 shuffles per 16 pairs).
-//   Tile pairs that contain excluded (1-2/1-3/1-4) pairs or the diagonal carry a 128x128 bit mask
-//   applied in registers.  The hot loop is the fast path w(d,k) = d at a clamped distance; the rare
-//   pairs closer than 1.9 A are corrected exactly, out of line.  Each item writes its partial
-//   forces to a scratch buffer; a second kernel sums, per atom, the partials of the tile pairs in
-//   its row and column in a fixed order and adds them to the gradient.
+//   Work item = (conformation, 128x128 atom tile pair J>=I), one one-warp CTA each, tile pairs ordered
+//   longest first.  A lane owns NI=4 i-atoms in registers for the whole tile; the 32 groups of 4 j-atoms
+//   rotate through the lanes together with their force accumulators (Newton's third law for 12 shuffles per
+//   16 pairs; diagonal tiles need only 17 of the 32 rotation steps).  Tile pairs that contain excluded
+//   (1-2/1-3/1-4) pairs or the diagonal carry a 128x128 bit mask applied in registers.  The hot loop is the
+//   fast path w(d,k) = d at a clamped distance, written in packed FP32 (FFMA2/FMUL2 over two j-atoms per
+//   instruction: the scalar version was issue-bound, the packed one is FMA-pipe-bound); the rare pairs closer
+//   than 1.9 A are corrected exactly, out of line.  Each item writes its partial forces to a scratch buffer;
+//   a second kernel sums, per atom, the partials of the tile pairs in its row and column in a fixed order and
+//   adds them to the gradient.  nb_kernel (scalar) is kept for comparison (MLP_NB_PACKED=0).
 #include "../../include/molearn_b200.h"
 #include "topology.hpp"
 
@@ -70,9 +72,6 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #ifndef NB_MINB
 #define NB_MINB 4    // resident warps per SM sub-partition the register budget is sized for (4 -> 128 registers)
 #endif
-#ifndef NB_UNROLL
-#define NB_UNROLL 1
-#endif
 constexpr float LJ_K = 1.9f, C_K = 0.4f;  // warp thresholds, torch_protein_energy.py:233-234
 constexpr float CLAMP = 0.999999f;        // acos clamp, :289
 constexpr size_t BONDED_SMEM_CAP = 100 * 1024;  // keep two CTAs per SM
@@ -94,7 +93,7 @@ struct mlp_energy {
     uint32_t nb_mode = 0;
     int N = 0, Npad = 0;
     // bonded
-    int n_tiles = 0, tile_atoms = 0, slot_stride = 0, max_cnt = 0, max_atoms = 0;
+    int n_tiles = 0, tile_atoms = 0, max_cnt = 0, max_atoms = 0;
     bool torsion_sines = false;    // some torsion phase is not 0 / pi: the kernel keeps the sine coefficients
     BTile* d_tiles = nullptr;
     int* d_halo = nullptr;
@@ -1260,7 +1259,7 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
     }
     const size_t smem = ((size_t)max_atoms + (size_t)max_cnt * stride + 1) * sizeof(float4);
     if (smem > BONDED_SMEM_CAP && tile_atoms > 32) return 1;
-    E->n_tiles = (int)tiles.size(); E->tile_atoms = tile_atoms; E->slot_stride = stride; E->max_cnt = max_cnt;
+    E->n_tiles = (int)tiles.size(); E->tile_atoms = tile_atoms; E->max_cnt = max_cnt;
     E->max_atoms = max_atoms; E->bonded_smem = smem;
     int rc;
     if ((rc = upload(E, &E->d_tiles, tiles))) return rc;
