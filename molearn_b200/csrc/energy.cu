@@ -847,24 +847,32 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
 
 // grad[b, n] (+)= w_nb[b] * (sum of the partial forces of every tile pair in n's tile row / column),
 // summed in list order: reproducible.
-__global__ void __launch_bounds__(NB_T)
+constexpr int RED_PARTS = 4;     // warps of a reduction CTA: each sums one contiguous quarter of an atom's block list
+__global__ void __launch_bounds__(32 * RED_PARTS)
 nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_off, const int* __restrict__ red_list,
                  int n_pairs, int N, float* __restrict__ grad, long sgb, long sgc, long sgn,
                  const float* __restrict__ weights, int accumulate, int skip_zero_weight) {
-    const int T = blockIdx.x, b = blockIdx.y, l = threadIdx.x;
-    const int n = T * NB_T + l;
+    // CTA = 32 consecutive atoms of one conformation; warp `part` sums its share of the tile's partial blocks,
+    // then part 0 adds the RED_PARTS sums in order: a fixed summation tree, reproducible, with 4x the loads in
+    // flight of a one-thread-per-atom loop (the kernel is latency-bound: 30 MB out of L2 for the headline batch)
+    __shared__ float s_part[RED_PARTS][3][32];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * 32 + lane;
+    const int T = (blockIdx.x * 32) / NB_T, l = (blockIdx.x * 32) % NB_T + lane;
     const float w = weights ? weights[4 * b + 3] : 1.f;
-    if (n >= N) return;
     float* g = grad + (long)b * sgb + (long)n * sgn;
     if (skip_zero_weight && w == 0.f) {          // nb_kernel wrote no partials for this conformation
-        if (!accumulate) { g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
+        if (part == 0 && n < N && !accumulate) { g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
         return;
     }
     float sx = 0.f, sy = 0.f, sz = 0.f;
     const float* base = fpart + (long)b * n_pairs * (6 * NB_T) + l;
     const int k0 = red_off[T], k1 = red_off[T + 1];
-    int k = k0;
-    for (; k + 4 <= k1; k += 4) {   // four independent block loads in flight; the order of the adds is fixed
+    const int per = (k1 - k0 + RED_PARTS - 1) / RED_PARTS;
+    const int ka = min(k1, k0 + part * per), kb = min(k1, ka + per);
+    int k = ka;
+    for (; k + 4 <= kb; k += 4) {
         float vx[4], vy[4], vz[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -875,13 +883,19 @@ nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_of
 #pragma unroll
         for (int u = 0; u < 4; ++u) { sx += vx[u]; sy += vy[u]; sz += vz[u]; }
     }
-    for (; k < k1; ++k) {
+    for (; k < kb; ++k) {
         const int e = red_list[k];
         const float* p = base + (long)(e >> 1) * (6 * NB_T) + (e & 1) * (3 * NB_T);
         sx += p[0]; sy += p[NB_T]; sz += p[2 * NB_T];
     }
-    if (accumulate) { g[0] = fmaf(w, sx, g[0]); g[sgc] = fmaf(w, sy, g[sgc]); g[2 * sgc] = fmaf(w, sz, g[2 * sgc]); }
-    else { g[0] = w * sx; g[sgc] = w * sy; g[2 * sgc] = w * sz; }
+    s_part[part][0][lane] = sx; s_part[part][1][lane] = sy; s_part[part][2][lane] = sz;
+    __syncthreads();
+    if (part == 0 && n < N) {
+#pragma unroll
+        for (int q = 1; q < RED_PARTS; ++q) { sx += s_part[q][0][lane]; sy += s_part[q][1][lane]; sz += s_part[q][2][lane]; }
+        if (accumulate) { g[0] = fmaf(w, sx, g[0]); g[sgc] = fmaf(w, sy, g[sgc]); g[2 * sgc] = fmaf(w, sz, g[2 * sgc]); }
+        else { g[0] = w * sx; g[sgc] = w * sy; g[2 * sgc] = w * sz; }
+    }
 }
 
 __global__ void zero_grad_kernel(float* __restrict__ grad, long sgb, long sgc, long sgn, int N, int B) {
@@ -1564,7 +1578,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         }
         if (grad) {
             prof_begin(3);
-            nb_reduce_kernel<<<dim3(e->n_nbt, (unsigned)B), NB_T, 0, stream>>>(fpart, e->d_red_off, e->d_red_list, e->n_pairs, N,
+            nb_reduce_kernel<<<dim3(e->n_nbt * (NB_T / 32), (unsigned)B), 32 * RED_PARTS, 0, stream>>>(fpart, e->d_red_off, e->d_red_list, e->n_pairs, N,
                 grad, sgb, sgc, sgn, weights, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0);
             prof_end(3);
             ++launches;
