@@ -228,7 +228,28 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
     s1.record()
     torch.cuda.synchronize()
     score_ms = s0.elapsed_time(s1)
-    return {"metric": "latent-grid points/sec (MurD, decode + 4 energy terms + RMSD to 16 frames)", "grid": G,
+    cpu = None
+    if rank == 0 and world == 1 and not getattr(run_scan, "skip_cpu", False):
+        # the reference's way, on the host cores, for a bounded sample of 16 grid points: decode on the CPU (same
+        # network), PyTorch CPU port of the energy, NumPy RMSD - scaled to points/s
+        from oracle.torch_port import TorchCPUPort
+        torch.set_num_threads(os.cpu_count() or 1)
+        net_cpu = AutoEncoder(out_points=frames.shape[1])
+        net_cpu.load_state_dict(net.state_dict())
+        net_cpu.eval()
+        port = TorchCPUPort(ma.physics().topology.as_dict())
+        zs = ma._encoded["grid"].reshape(-1, 2)[:: (G * G) // 16][:16]
+        tgt = torch.from_numpy(frames)
+        c0 = time.perf_counter()
+        with torch.no_grad():
+            dec = net_cpu.decode(zs)[:, :frames.shape[1], :] * data.std + data.mean
+            xr = dec.permute(0, 2, 1).contiguous()
+            e_cpu = torch.stack(list(port.bonded(xr)) + [port.nonbonded(xr)])
+            r_cpu = ((dec.unsqueeze(1) - tgt.unsqueeze(0)) ** 2).sum(-1).mean(-1).sqrt()
+        c1 = time.perf_counter() - c0
+        cpu = {"value": 16 / c1, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"16 of the {G * G} grid points: CPU decode + PyTorch CPU port energy (forward) + NumPy-style RMSD, {c1:.2f} s"}
+    return {"metric": "latent-grid points/sec (MurD, decode + 4 energy terms + RMSD to 16 frames)", "grid": G, "cpu_baseline": cpu,
             "value": G * G / (ms * 1e-3), "unit": "points/s", "ms": ms, "scaling": "strong", "n_gpus": world,
             "columns": int(rows.shape[1]), "gather_bytes": ma.scan_stats["gather_bytes"],
             "points_this_rank": ma.scan_stats["points_this_rank"],
@@ -336,7 +357,22 @@ def run_config4(dev, info, frames, pk):
     nb_ms = pr["nb"][0] / pr["nb"][1]
     flops = FLOPS_PER_PAIR * tpe.topology.n_nb_pairs * BB
     peak = 148 * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-    return {"n_atoms": tpe.n_atoms, "batch": BB, "conformations_per_s": BB / (ms * 1e-3), "ms_per_step": ms,
+    cpu = None
+    try:   # the reference cannot hold [128,N,N]: one conformation at a time (three dense [N,N] fp32 tables + autograd, ~7 GB)
+        from oracle.torch_port import TorchCPUPort
+        torch.set_num_threads(os.cpu_count() or 1)
+        port = TorchCPUPort(tpe.topology.as_dict())
+        x1 = torch.from_numpy(x[:1]).permute(0, 2, 1).contiguous()
+        port.energy_and_grad(x1)
+        c0 = time.perf_counter()
+        port.energy_and_grad(x1)
+        c1 = time.perf_counter() - c0
+        cpu = {"value": 1.0 / c1, "unit": "conformations/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 of the {BB} conformations, fwd+bwd of all four terms, {c1:.2f} s"}
+        del port
+    except Exception as exc:                      # e.g. not enough host memory
+        cpu = {"unavailable": str(exc)[:200]}
+    return {"n_atoms": tpe.n_atoms, "batch": BB, "conformations_per_s": BB / (ms * 1e-3), "ms_per_step": ms, "cpu_baseline": cpu,
             "pairs_per_s": tpe.topology.n_nb_pairs * BB / (nb_ms * 1e-3), "nb_kernel_ms": nb_ms,
             "nb_fp32_frac": flops / (nb_ms * 1e-3) / 1e12 / peak, "bonded_kernel_ms": pr["bonded"][0] / pr["bonded"][1],
             "nb_reduce_ms": pr["nb_reduce"][0] / pr["nb_reduce"][1], "info": dv.info(),
@@ -531,6 +567,7 @@ def main():
     }
 
     # ---- latent-grid scan (BASELINE config 3): sharded over the ranks, one all-gather --------------
+    run_scan.skip_cpu = args.no_cpu_baseline
     if not args.no_extras and not args.bonded_only:
         out["scan"] = run_scan(dev, rank, world, info, frames, args.scan_grid, barrier)
 
