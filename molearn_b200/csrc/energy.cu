@@ -46,7 +46,10 @@
 // ------------------------------------------------------------------------------------------
 // constants
 // ------------------------------------------------------------------------------------------
-constexpr int BT = 256;          // bonded: threads per CTA
+#ifndef BONDED_THREADS
+#define BONDED_THREADS 128
+#endif
+constexpr int BT = BONDED_THREADS;  // bonded: threads per CTA = atoms per tile
 constexpr int RB = 2, RA = 2, RT = 2;  // bonded: max bonds / angles / torsions per thread
 constexpr int SLOT_STRIDE = BT + 1;  // odd stride (in float4s): an atom's consecutive slots fall into different banks
 constexpr int PF = 4;            // bonded: coordinate elements staged per thread (3*(own+halo) <= PF*BT)
@@ -58,7 +61,7 @@ constexpr int NB_NI = 4;         // i-atoms per lane
 #endif
 constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each (1: a finished item frees its slot at once)
 #ifndef BONDED_MINB
-#define BONDED_MINB 2   // bonded CTAs per SM the register budget is sized for
+#define BONDED_MINB 4   // bonded CTAs per SM the register budget is sized for (4 x 128 threads x 128 registers)
 #endif
 #ifndef NB2_MINB
 #define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
@@ -74,7 +77,7 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #endif
 constexpr float LJ_K = 1.9f, C_K = 0.4f;  // warp thresholds, torch_protein_energy.py:233-234
 constexpr float CLAMP = 0.999999f;        // acos clamp, :289
-constexpr size_t BONDED_SMEM_CAP = 100 * 1024;  // keep two CTAs per SM
+constexpr size_t BONDED_SMEM_CAP = 54 * 1024;   // keep four CTAs per SM
 
 struct BondRec { uint32_t ij, slots; float r0, k; };                       // 16 B
 struct AngleRec { uint32_t ij, k, s_ij, s_k; float th0, kf, pad0, pad1; }; // 32 B
@@ -1272,7 +1275,9 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
         tiles.push_back(bt);
     }
     const size_t smem = ((size_t)max_atoms + (size_t)max_cnt * stride + 1) * sizeof(float4);
-    if (smem > BONDED_SMEM_CAP && tile_atoms > 32) return 1;
+    if (smem > 200 * 1024) { mlp_set_error("pack_bonded: too many gradient contributions per atom for the shared-memory slot table"); return MLP_E_ARG; }
+    // (above BONDED_SMEM_CAP fewer CTAs fit per SM; the slot stride is a compile-time constant, so a smaller
+    //  tile would not shrink the table)
     E->n_tiles = (int)tiles.size(); E->tile_atoms = tile_atoms; E->max_cnt = max_cnt;
     E->max_atoms = max_atoms; E->bonded_smem = smem;
     int rc;
