@@ -110,6 +110,8 @@ struct mlp_energy {
     int n_pairs = 0, n_masked = 0; // tile pairs (masked ones first)
     int4* d_pairs = nullptr;       // (I, J, mask index or -1, rotation steps), longest items first
     uint32_t* d_masks = nullptr;   // [n_masked][32 groups][32 lanes] uint16 pair masks
+    uint32_t* d_stepbits = nullptr; // [n_masked] bit r: rotation step r touches an excluded pair
+    float2* d_parw = nullptr;      // [Npad] (a, b) product-form LJ parameters of the packed repulsive kernel
     float* d_q = nullptr;          // [Npad]
     float2* d_par = nullptr;       // [Npad] (R/2, sqrt(12 eps))
     int* d_red_off = nullptr;      // [n_nbt+1] per tile: range in d_red_list
@@ -523,7 +525,8 @@ __device__ __forceinline__ bool nb_micro(const float4 (&xi)[NB_NI], const float2
 }
 
 // Correction pass over a micro-tile that holds at least one pair closer than sqrt(NB_THR2).
-template <bool MASKED, bool FULL>
+// WFORM: the per-atom parameters are (a, b) of nb_micro2's product form, R_ij (12 eps_ij)^(1/12) = a_i b_j + b_i a_j.
+template <bool MASKED, bool FULL, bool WFORM = false>
 __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
                                              const float2 (&pj)[4], uint32_t m16,
                                              float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
@@ -549,7 +552,9 @@ __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const fl
             bool on = !MASKED || ((m16 >> (4 * a + b)) & 1u);
             // NaN coordinates: !(r2 >= thr) is true -> exact path -> NaN propagates
             if (on && !(r2 >= NB_THR2)) {
-                float3 c = nb_pair_fix<FULL>(r2, pi[a].x + pj[b].x, pi[a].y * pj[b].y, yi[a].w * yj[b].w);
+                const float Rij = WFORM ? fmaf(pi[a].y, pj[b].x, pi[a].x * pj[b].y) : pi[a].x + pj[b].x;
+                const float e12 = WFORM ? 1.f : pi[a].y * pj[b].y;
+                float3 c = nb_pair_fix<FULL>(r2, Rij, e12, yi[a].w * yj[b].w);
                 Fi[a].x = fmaf(c.x, dx, Fi[a].x); Fi[a].y = fmaf(c.x, dy, Fi[a].y); Fi[a].z = fmaf(c.x, dz, Fi[a].z);
                 Fj[b].x = fmaf(c.x, dx, Fj[b].x); Fj[b].y = fmaf(c.x, dy, Fj[b].y); Fj[b].z = fmaf(c.x, dz, Fj[b].z);
                 Sl += c.y; Sc += c.z;
@@ -669,7 +674,14 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
 // pipe), so here every FMA-pipe operation of the pair term is packed over two j-atoms: j data sit in shared
 // memory component-wise (x[128], y[128], ...), a lane reads float4s = two (j, j+1) pairs per component; the
 // lane's i-atoms are kept duplicated (v, v) in registers; i-force accumulators are (even-j, odd-j) partial
-// sums folded at the end of the item.  Same arithmetic per pair as nb_pair_fast (bit-identical results).
+// sums folded at the end of the item.  Same arithmetic per pair as nb_pair_fast.
+// NB_WFORM (repulsive mode only): the Lennard-Jones pair parameters are folded into one length,
+//   12 eps_ij (R_ij/d)^12 = (w_ij/d)^12,  w_ij = (12 eps_ij)^(1/12) R_ij = a_i b_j + b_i a_j,
+//   b = (12 eps)^(1/24), a = b R/2   (eps_ij = sqrt(eps_i eps_j), R_ij = R_i/2 + R_j/2; utils.py:814-815),
+// which is 2 FMA-pipe operations per pair instead of 4 (R_ij, eps_ij, R_ij/d, eps_ij t^6): 26 instead of 27 per pair.
+#ifndef NB_WFORM
+#define NB_WFORM 1
+#endif
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
 
@@ -677,6 +689,7 @@ template <bool GRAD, bool MASKED, bool FULL>
 __device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const float2 (&hRi)[NB_NI], const float2 (&sei)[NB_NI],
                                            const float4 (&cj)[6], uint32_t m16,
                                            float2 (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
+    constexpr bool WF = NB_WFORM && !FULL;
     float rmin = 3.0e38f;
     const float2 neg1 = dup(-1.f), one = dup(1.f);
 #pragma unroll
@@ -691,13 +704,15 @@ __device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const fl
         for (int a = 0; a < NB_NI; ++a) {
             float2 dx = __ffma2_rn(xj, neg1, xi[a][0]), dy = __ffma2_rn(yj, neg1, xi[a][1]), dz = __ffma2_rn(zj, neg1, xi[a][2]);
             float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-            float2 e12 = __fmul2_rn(sei[a], sj);
+            // WF: (hRi, sei) = (a_i, b_i), (hj, sj) = (a_j, b_j); e12 holds w_ij
+            float2 e12 = WF ? __ffma2_rn(sei[a], hj, __fmul2_rn(hRi[a], sj)) : __fmul2_rn(sei[a], sj);
             float2 qq = __fmul2_rn(xi[a][3], qj);
-            float2 Rij = __ffma2_rn(hRi[a], one, hj);          // add.f32x2 is lowered to two FADDs; FFMA2 by one stays packed
+            float2 Rij = WF ? e12 : __ffma2_rn(hRi[a], one, hj);   // add.f32x2 is lowered to two FADDs; FFMA2 by one stays packed
             if (MASKED) {
                 const bool on0 = (m16 >> (4 * a + 2 * p)) & 1u, on1 = (m16 >> (4 * a + 2 * p + 1)) & 1u;
                 r2.x = on0 ? r2.x : NB_MASKED_R2; r2.y = on1 ? r2.y : NB_MASKED_R2;
-                e12.x = on0 ? e12.x : 0.f; e12.y = on1 ? e12.y : 0.f;
+                if (WF) { Rij.x = on0 ? Rij.x : 0.f; Rij.y = on1 ? Rij.y : 0.f; }
+                else { e12.x = on0 ? e12.x : 0.f; e12.y = on1 ? e12.y : 0.f; }
                 qq.x = on0 ? qq.x : 0.f; qq.y = on1 ? qq.y : 0.f;
             }
             rmin = fmin3(rmin, r2.x, r2.y);
@@ -706,7 +721,7 @@ __device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const fl
             float2 t = __fmul2_rn(Rij, inv);
             float2 t2 = __fmul2_rn(t, t);
             float2 t6 = __fmul2_rn(__fmul2_rn(t2, t2), t2);
-            float2 u6 = __fmul2_rn(e12, t6);
+            float2 u6 = WF ? t6 : __fmul2_rn(e12, t6);
             float2 ec = __fmul2_rn(qq, inv);
             float2 u;
             if (FULL) {
@@ -735,7 +750,7 @@ template <bool GRAD, bool FULL>
 __global__ void __launch_bounds__(32, 4 * NB2_MINB)
 nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const float* __restrict__ q, int N,
            const float2* __restrict__ par, const int4* __restrict__ pairs,
-           const uint32_t* __restrict__ masks, int n_pairs, int B,
+           const uint32_t* __restrict__ masks, const uint32_t* __restrict__ stepbits, int n_pairs, int B,
            float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
     __shared__ float4 s_j[6][32];                 // component c of the 128 j-atoms: s_j[c][g] = atoms 4g..4g+3
     __shared__ uint32_t s_m[NB_T * 4];            // uint16 [g][lane] pair masks, as words
@@ -784,14 +799,18 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     const int src_lane = (lane + 1) & 31;
     const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m);
     const int n_steps = IJ.w;
+    // bit r: rotation step r of this tile pair has an excluded pair in some lane (a band tile has 3 such steps of 32,
+    // a diagonal tile 4-5 of 17 for backbone systems); the other steps run the mask-free micro-tile
+    const uint32_t sbits = masked ? stepbits[IJ.z] : 0u;
 #pragma unroll 1
     for (int r = 0; r < n_steps; ++r) {
         const int g = (lane + r) & 31;
         float4 cj[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) cj[c] = s_j[c][g];
-        const uint32_t m16 = masked ? sm16[g * 32 + lane] : 0xffffu;
-        const bool close = masked ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
+        const bool mstep = (sbits >> r) & 1u;
+        const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
+        const bool close = mstep ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
                                   : nb_micro2<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
         if (close) {
             // rare: exact correction through the scalar path (un-packed views of the same data)
@@ -812,8 +831,7 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
                 upj[bb] = make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
                 dFj[bb] = make_float3(0.f, 0.f, 0.f);
             }
-            if (masked) nb_micro_fix<true, FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
-            else nb_micro_fix<false, FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+            nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
 #pragma unroll
             for (int a = 0; a < NB_NI; ++a) { Fi[a][0].x += dFi[a].x; Fi[a][1].x += dFi[a].y; Fi[a][2].x += dFi[a].z; }
             Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
@@ -1295,11 +1313,13 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     const int nt = (N + NB_T - 1) / NB_T;
     E->n_nbt = nt; E->Npad = nt * NB_T;
     std::vector<float> q(E->Npad, 0.f);
-    std::vector<float2> par(E->Npad, make_float2(1.f, 0.f));
+    std::vector<float2> par(E->Npad, make_float2(1.f, 0.f)), parw(E->Npad, make_float2(0.f, 0.f));
     for (int i = 0; i < N; ++i) {
         q[i] = (float)T.charges[i];
         // R_ij = |R_i+R_j|/2, eps_ij = sqrt(eps_i eps_j) (utils.py:814-815); 12 folded into eps
         par[i] = make_float2(0.5f * T.vdw_R[i], (float)std::sqrt(12.0 * (double)T.vdw_e[i]));
+        const double bw = std::pow(12.0 * (double)T.vdw_e[i], 1.0 / 24.0);   // 0 for eps = 0
+        parw[i] = make_float2((float)(bw * 0.5 * (double)T.vdw_R[i]), (float)bw);
     }
     // exclusions per tile pair
     std::map<std::pair<int, int>, std::vector<std::pair<int, int>>> ex;
@@ -1309,7 +1329,7 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     }
     for (int t = 0; t < nt; ++t) ex[{t, t}];  // diagonal tiles are always masked (j > i)
     std::vector<int4> band, clean, diag;
-    std::vector<uint32_t> masks;
+    std::vector<uint32_t> masks, stepbits;
     for (auto& kv : ex) {
         const int I = kv.first.first, J = kv.first.second;
         // uint16 [g][lane]: bit 4a+b <-> pair (i = 4*lane+a, j = 4g+b) allowed
@@ -1334,6 +1354,11 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
         std::vector<uint32_t> m((size_t)NB_T * 4);
         std::memcpy(m.data(), m16.data(), m.size() * sizeof(uint32_t));
         masks.insert(masks.end(), m.begin(), m.end());
+        uint32_t sb = 0;
+        for (int g = 0; g < 32; ++g)
+            for (int ln = 0; ln < 32; ++ln)
+                if (m16[(size_t)g * 32 + ln] != 0xffffu) sb |= 1u << ((g - ln) & 31);   // lane ln meets group g at step (g - ln) mod 32
+        stepbits.push_back(sb);
         (I == J ? diag : band).push_back(make_int4(I, J, mi, I == J ? 17 : 32));
     }
     E->n_masked = (int)(band.size() + diag.size());
@@ -1358,6 +1383,8 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     int rc;
     if ((rc = upload(E, &E->d_pairs, pairs))) return rc;
     if ((rc = upload(E, &E->d_masks, masks))) return rc;
+    if ((rc = upload(E, &E->d_stepbits, stepbits))) return rc;
+    if ((rc = upload(E, &E->d_parw, parw))) return rc;
     if ((rc = upload(E, &E->d_q, q))) return rc;
     if ((rc = upload(E, &E->d_par, par))) return rc;
     if ((rc = upload(E, &E->d_red_off, red_off))) return rc;
@@ -1559,7 +1586,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         const bool full = e->nb_mode == MLP_NB_FULL;
         double* ep = energies ? e_nb : nullptr;
 #define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
-#define NB_LAUNCH2(G, F) nb_kernel2<G, F><<<(unsigned)items, 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
+#define NB_LAUNCH2(G, F) nb_kernel2<G, F><<<(unsigned)items, 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, (int)B, fpart, weights, ep)
         if (e->packed) {
             if (grad) { if (full) NB_LAUNCH2(true, true); else NB_LAUNCH2(true, false); }
             else { if (full) NB_LAUNCH2(false, true); else NB_LAUNCH2(false, false); }
