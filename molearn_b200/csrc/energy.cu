@@ -280,8 +280,8 @@ template <bool GRAD, bool SG>
 __global__ void __launch_bounds__(BT, BONDED_MINB)
 bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, const BondRec* __restrict__ bonds,
               const AngleRec* __restrict__ angles, const TorsRec* __restrict__ tors, const int* __restrict__ cnts,
-              const float* __restrict__ x, long sxb, long sxc, long sxn,
-              float* __restrict__ grad, long sgb, long sgc, long sgn,
+              const float* __restrict__ x, long sxb, int sxc, int sxn,
+              float* __restrict__ grad, long sgb, int sgc, int sgn,
               const float* __restrict__ weights, float* __restrict__ e_part /* [B][n_tiles][3] or null */,
               int B, int conf_per_cta, uint32_t term_mask, int accumulate, int max_atoms, int max_cnt) {
     constexpr int STRIDE = SLOT_STRIDE;  // slot (atom a, k-th contribution) at k*STRIDE + a
@@ -315,7 +315,9 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
     }
 
     // coordinate staging plan: element e = tid + q*BT of the tile's 3*(own+halo) floats
-    long goff[PF];
+    // element offsets inside one conformation are 32-bit (the host checks the extent): a 64-bit multiply-add
+    // per staged element and per stored gradient component was 10 % of the kernel's instructions
+    int goff[PF];
     int sidx[PF];
     {
         const int n_el = 3 * (t.n_own + t.n_halo);
@@ -334,7 +336,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
                     la = t.n_own + h / 3; c = h - 3 * (h / 3);
                 }
                 int ga = la < t.n_own ? t.a0 + la : halo[t.halo_off + la - t.n_own];
-                goff[q] = c * sxc + (long)ga * sxn;
+                goff[q] = c * sxc + ga * sxn;
                 sidx[q] = 4 * la + c;
             }
         }
@@ -344,20 +346,22 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
     const int b0 = blockIdx.y * conf_per_cta;
     const int b1 = min(B, b0 + conf_per_cta);
     float pf[PF];
-    auto prefetch = [&](int b) {
-        const float* xb = x + (long)b * sxb;
+    auto prefetch = [&](const float* xb) {
 #pragma unroll
         for (int q = 0; q < PF; ++q) if (sidx[q] >= 0) pf[q] = xb[goff[q]];
     };
+    const float* xb = x + (long)b0 * sxb;                 // conformation b (running pointers: no per-element 64-bit multiply)
+    float* gb = GRAD ? grad + (long)b0 * sgb : nullptr;
+    const int gofs = (t.a0 + tid) * sgn;
     const bool do_b = term_mask & MLP_TERM_BOND, do_a = term_mask & MLP_TERM_ANGLE, do_t = term_mask & MLP_TERM_TORSION;
 
-    if (b0 < b1) prefetch(b0);
-    for (int b = b0; b < b1; ++b) {
+    if (b0 < b1) prefetch(xb);
+    for (int b = b0; b < b1; ++b, xb += sxb, gb += sgb) {
         float wb = 1.f, wa = 1.f, wt = 1.f;
         if (weights) { wb = weights[4 * b]; wa = weights[4 * b + 1]; wt = weights[4 * b + 2]; }
         if (GRAD && accumulate && !e_part && (!do_b || wb == 0.f) && (!do_a || wa == 0.f) && (!do_t || wt == 0.f)) {
             // backward correction with nothing to add for this conformation (CTA-uniform)
-            if (b + 1 < b1) prefetch(b + 1);
+            if (b + 1 < b1) prefetch(xb + sxb);
             continue;
         }
         // stage coordinates (the previous iteration's term phase is over: everybody passed its second barrier)
@@ -366,7 +370,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
         if (GRAD && term_mask != MLP_TERM_BONDED)
             for (int s = tid; s < max_cnt * STRIDE; s += BT) slots[s] = make_float4(0.f, 0.f, 0.f, 0.f);  // rare: a term type is off
         __syncthreads();
-        if (b + 1 < b1) prefetch(b + 1);
+        if (b + 1 < b1) prefetch(xb + sxb);
 
         float eb = 0.f, ea = 0.f, et = 0.f;
         if (do_b) {
@@ -401,7 +405,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
                 gx += (v0.x + v1.x) + (v2.x + v3.x); gy += (v0.y + v1.y) + (v2.y + v3.y); gz += (v0.z + v1.z) + (v2.z + v3.z);
             }
             if (tid < t.n_own) {
-                float* g = grad + (long)b * sgb + (long)(t.a0 + tid) * sgn;
+                float* g = gb + gofs;
                 if (accumulate) { g[0] += gx; g[sgc] += gy; g[2 * sgc] += gz; }
                 else { g[0] = gx; g[sgc] = gy; g[2 * sgc] = gz; }
             }
@@ -624,9 +628,9 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
 
     // Diagonal tile: block (L,g) mirrors block (g,L), so 17 of the 32 rotation steps visit every unordered
     // block pair once (step 0 = the in-block triangle, step 16 = lanes < 16 only; the masks encode both).
-    const int n_steps = IJ.w;
+    const int r_begin = IJ.w & 0xff, n_steps = IJ.w >> 8;    // rotation steps [r_begin, n_steps) of this tile pair
 #pragma unroll 1
-    for (int r = 0; r < n_steps; ++r) {
+    for (int r = r_begin; r < n_steps; ++r) {
         const int g = (lane + r) & 31;
         float4 xj[4];
         float2 pj[4];
@@ -679,6 +683,9 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
 //   12 eps_ij (R_ij/d)^12 = (w_ij/d)^12,  w_ij = (12 eps_ij)^(1/12) R_ij = a_i b_j + b_i a_j,
 //   b = (12 eps)^(1/24), a = b R/2   (eps_ij = sqrt(eps_i eps_j), R_ij = R_i/2 + R_j/2; utils.py:814-815),
 // which is 2 FMA-pipe operations per pair instead of 4 (R_ij, eps_ij, R_ij/d, eps_ij t^6): 26 instead of 27 per pair.
+#ifndef NB_DIAG_SPLIT
+#define NB_DIAG_SPLIT 2
+#endif
 #ifndef NB_WFORM
 #define NB_WFORM 1
 #endif
@@ -798,12 +805,12 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     for (int pp = 0; pp < 2; ++pp) Fj[pp][0] = Fj[pp][1] = Fj[pp][2] = dup(0.f);
     const int src_lane = (lane + 1) & 31;
     const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m);
-    const int n_steps = IJ.w;
+    const int r_begin = IJ.w & 0xff, n_steps = IJ.w >> 8;    // rotation steps [r_begin, n_steps) of this tile pair
     // bit r: rotation step r of this tile pair has an excluded pair in some lane (a band tile has 3 such steps of 32,
     // a diagonal tile 4-5 of 17 for backbone systems); the other steps run the mask-free micro-tile
     const uint32_t sbits = masked ? stepbits[IJ.z] : 0u;
 #pragma unroll 1
-    for (int r = 0; r < n_steps; ++r) {
+    for (int r = r_begin; r < n_steps; ++r) {
         const int g = (lane + r) & 31;
         float4 cj[6];
 #pragma unroll
@@ -1359,12 +1366,19 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
             for (int ln = 0; ln < 32; ++ln)
                 if (m16[(size_t)g * 32 + ln] != 0xffffu) sb |= 1u << ((g - ln) & 31);   // lane ln meets group g at step (g - ln) mod 32
         stepbits.push_back(sb);
-        (I == J ? diag : band).push_back(make_int4(I, J, mi, I == J ? 17 : 32));
+        if (I == J) {
+            // diagonal tiles run rotation steps 0..16; they are the last (shortest) items of the launch and are cut
+            // into NB_DIAG_SPLIT step ranges, each with its own partial block, to shorten the tail of the last wave
+            for (int k = 0; k < NB_DIAG_SPLIT; ++k) {
+                const int r0 = 17 * k / NB_DIAG_SPLIT, r1 = 17 * (k + 1) / NB_DIAG_SPLIT;
+                diag.push_back(make_int4(I, J, mi, r0 | (r1 << 8)));
+            }
+        } else band.push_back(make_int4(I, J, mi, 32 << 8));
     }
     E->n_masked = (int)(band.size() + diag.size());
     for (int I = 0; I < nt; ++I)
         for (int J = I; J < nt; ++J)
-            if (!ex.count({I, J})) clean.push_back(make_int4(I, J, -1, 32));
+            if (!ex.count({I, J})) clean.push_back(make_int4(I, J, -1, 32 << 8));
     std::vector<int4> pairs(band);
     pairs.insert(pairs.end(), clean.begin(), clean.end());
     pairs.insert(pairs.end(), diag.begin(), diag.end());
@@ -1562,11 +1576,17 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         bstream = e->side;
     }
     if (bonded) {
+        auto fits = [&](int64_t sc, int64_t sn) { return sc >= 0 && sn >= 0 && (int64_t)(N - 1) * sn + 2 * sc < ((int64_t)1 << 31); };
+        if (!fits(sxc, sxn) || (grad && !fits(sgc, sgn))) {
+            mlp_set_error("mlp_energy_eval: the bonded kernel addresses one conformation with 32-bit element offsets "
+                          "(strides must be non-negative and a conformation must span less than 2^31 elements)");
+            return MLP_E_ARG;
+        }
         prof_begin(1);
         int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
         dim3 grid(e->n_tiles, (unsigned)((B + cpc - 1) / cpc));
 #define BONDED_LAUNCH(G, S) bonded_kernel<G, S><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt, \
-            x, sxb, sxc, sxn, grad, sgb, sgc, sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc, \
+            x, sxb, (int)sxc, (int)sxn, grad, sgb, (int)sgc, (int)sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc, \
             term_mask & MLP_TERM_BONDED, grad ? (int)accumulate : 0, e->max_atoms, e->max_cnt)
         if (grad) { if (e->torsion_sines) BONDED_LAUNCH(true, true); else BONDED_LAUNCH(true, false); }
         else { if (e->torsion_sines) BONDED_LAUNCH(false, true); else BONDED_LAUNCH(false, false); }
