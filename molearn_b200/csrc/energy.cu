@@ -39,6 +39,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -50,7 +51,7 @@
 #define BONDED_THREADS 128
 #endif
 constexpr int BT = BONDED_THREADS;  // bonded: threads per CTA = atoms per tile
-constexpr int RB = 2, RA = 2, RT = 2;  // bonded: max bonds / angles / torsions per thread
+constexpr int RI = 2;            // bonded: max work items per thread
 constexpr int SLOT_STRIDE = BT + 1;  // odd stride (in float4s): an atom's consecutive slots fall into different banks
 constexpr int PF = 4;            // bonded: coordinate elements staged per thread (3*(own+halo) <= PF*BT)
 constexpr int NF = 4;            // torsion Fourier orders kept (ff14SB periods are 1..4)
@@ -61,7 +62,7 @@ constexpr int NB_NI = 4;         // i-atoms per lane
 #endif
 constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each (1: a finished item frees its slot at once)
 #ifndef BONDED_MINB
-#define BONDED_MINB 4   // bonded CTAs per SM the register budget is sized for (4 x 128 threads x 128 registers)
+#define BONDED_MINB 5   // bonded CTAs per SM the register budget is sized for (5 x 128 threads x 96 registers)
 #endif
 #ifndef NB2_MINB
 #define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
@@ -79,15 +80,21 @@ constexpr float LJ_K = 1.9f, C_K = 0.4f;  // warp thresholds, torch_protein_ener
 constexpr float CLAMP = 0.999999f;        // acos clamp, :289
 constexpr size_t BONDED_SMEM_CAP = 54 * 1024;   // keep four CTAs per SM
 
-struct BondRec { uint32_t ij, slots; float r0, k; };                       // 16 B
-struct AngleRec { uint32_t ij, k, s_ij, s_k; float th0, kf, pad0, pad1; }; // 32 B
-struct TorsRec { uint32_t ij, kl, s_ij, s_kl; float c0, cg[NF], sg[NF], pad[3]; };  // 64 B
-static_assert(sizeof(BondRec) == 16 && sizeof(AngleRec) == 32 && sizeof(TorsRec) == 64, "record layout");
-constexpr uint32_t OWNER = 0x8000u;  // bit 15 of the first local index: this tile counts the energy
+// one bonded work item: torsion (i,j,k,l) + angle (i,j,k) + bond (i,j)|(j,k), any subset (flags)
+struct ItemRec {
+    uint32_t ij, kl;          // local atom indices, 16 bits each
+    uint32_t s_ij, s_kl;      // gradient slot ids of the four atoms, 16 bits each
+    float c0, cg[NF];         // torsion Fourier series (cosine coefficients)
+    float th0, ka, r0, kb;    // angle (theta0, K), bond (r0, K)
+    uint32_t flags, pad[2];
+};
+static_assert(sizeof(ItemRec) == 64, "record layout");
+constexpr uint32_t IT_T = 1u, IT_A = 2u, IT_B = 4u, IT_B_JK = 8u;       // which terms the item carries; bond on (j,k)
+constexpr uint32_t IT_OWN_T = 16u, IT_OWN_A = 32u, IT_OWN_B = 64u;      // this tile counts the term's energy
 
 struct BTile {
     int a0, n_own, n_halo, halo_off;
-    int bond_off, n_bond, angle_off, n_angle, tors_off, n_tors;  // counts are padded to multiples of 32
+    int item_off, n_item;            // padded to a multiple of 32
     int cnt_off, pad;
 };
 
@@ -97,12 +104,12 @@ struct mlp_energy {
     int N = 0, Npad = 0;
     // bonded
     int n_tiles = 0, tile_atoms = 0, max_cnt = 0, max_atoms = 0;
+    long n_items = 0;              // bonded work items over all tiles (boundary items are evaluated by each tile they touch)
     bool torsion_sines = false;    // some torsion phase is not 0 / pi: the kernel keeps the sine coefficients
     BTile* d_tiles = nullptr;
     int* d_halo = nullptr;
-    BondRec* d_bonds = nullptr;
-    AngleRec* d_angles = nullptr;
-    TorsRec* d_tors = nullptr;
+    ItemRec* d_items = nullptr;
+    float4* d_sg = nullptr;        // [items] torsion sine coefficients (only read when torsion_sines)
     int* d_cnt = nullptr;
     size_t bonded_smem = 0;
     // non-bonded
@@ -177,109 +184,115 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------
 // bonded kernel
 // ------------------------------------------------------------------------------------------
-// E = K (|ri-rj| - r0)^2                      (torch_protein_energy.py:282-284)
-template <bool GRAD>
-__device__ __forceinline__ void bond_term(const float4* sc, float4* slots, const BondRec& r, float w, float& e) {
-    const uint32_t i = r.ij & 0x7fffu, j = r.ij >> 16;
-    float3 v = f3(sc[i]) - f3(sc[j]);
-    float d2 = dot(v, v);
-    float inv = d2 > 0.f ? rsqrt_nr(d2) : 0.f;   // autograd: d|v|/dv = 0 at v = 0
-    float d = d2 * inv;
-    d = d2 != d2 ? d2 : d;
-    float dl = d - r.r0;
-    float kdl = r.k * dl;
-    if (r.ij & OWNER) e = fmaf(kdl, dl, e);
-    if (GRAD) {
-        float3 g = (2.f * w * kdl * inv) * v;
-        slots[r.slots & 0xffffu] = f4(g);
-        slots[r.slots >> 16] = f4(-1.f * g);
-    }
-}
-
-// theta = acos(clamp(v1.v2/(|v1||v2|))), E = K (theta-theta0)^2      (:286-293)
-template <bool GRAD>
-__device__ __forceinline__ void angle_term(const float4* sc, float4* slots, const AngleRec& r, float w, float& e) {
-    const uint32_t i = r.ij & 0x7fffu, j = r.ij >> 16, k = r.k;
-    float3 rj = f3(sc[j]);
-    float3 v1 = f3(sc[i]) - rj, v2 = f3(sc[k]) - rj;
-    float n1 = dot(v1, v1), n2 = dot(v2, v2);
-    float c = dot(v1, v2) * rsqrt_nr(n1 * n2);
-    float cc = fminf(fmaxf(c, -CLAMP), CLAMP);
-    float th = acosf(cc);
-    if (c != c) th = c;  // NaN propagates (fminf/fmaxf would swallow it)
-    float dt = th - r.th0;
-    float kdt = r.kf * dt;
-    if (r.ij & OWNER) e = fmaf(kdt, dt, e);
-    if (GRAD) {
-        // dtheta/dv1 = v1 x (v1 x v2) / (|v1|^2 |v1 x v2|), dtheta/dv2 = -v2 x (v1 x v2) / (|v2|^2 |v1 x v2|):
-        // the cross-product form of -1/sqrt(1-c^2) * dc/dv, which does not cancel near c = +-1.
-        // torch.clamp passes no gradient outside the clamp, so the term is dropped there.
-        float3 n = cross(v1, v2);
-        float nn = dot(n, n);
-        float coef = (c > -CLAMP && c < CLAMP) ? 2.f * w * kdt * rsqrt_fast(nn) : 0.f;
-        if (c != c) coef = c;
-        float3 gi = (coef * rcp_fast(n1)) * cross(v1, n);
-        float3 gk = (-coef * rcp_fast(n2)) * cross(v2, n);
-        slots[r.s_ij & 0xffffu] = f4(gi);
-        slots[r.s_k] = f4(gk);
-        slots[r.s_ij >> 16] = f4(-1.f * (gi + gk));
-    }
-}
-
-// phi = atan2(b2.(c32 x c12), |b2| c12.c32), E = sum_p (V/f)(1+cos(n phi - gamma))   (:295-304)
-// evaluated as a Fourier series in (cos phi, sin phi) - no atan2 / cos calls.
+// One work item = up to one torsion (i,j,k,l), one angle (i,j,k) and one bond ((i,j) or (j,k)) on the SAME
+// four atoms (pack_bonded matches every angle to a torsion that contains it and every bond to an item that
+// contains it; torsions are reversed where needed - phi(i,j,k,l) = phi(l,k,j,i)).  The three terms share the
+// four coordinate reads, F = ri-rj, G = rj-rk, A = F x G and the squared lengths, and their gradients are summed
+// in registers: 4 shared-memory reads and 4 slot writes per item instead of 9 + 9 for three separate terms.
+// (The separate-term kernel was bound by the shared-memory pipe: 78 % LSU wavefront utilisation.)
+//   bond   E = K (|v| - r0)^2                                      (torch_protein_energy.py:282-284)
+//   angle  theta = acos(clamp(v1.v2/(|v1||v2|))), E = K (theta-theta0)^2                  (:286-293)
+//   torsion phi = atan2(b2.(c32 x c12), |b2| c12.c32), E = sum_p (V/f)(1+cos(n phi - gamma)) (:295-304),
+//          evaluated as a Fourier series in (cos phi, sin phi) - no atan2 / cos calls.
 // SG: the series has sine coefficients (phases other than 0 / pi).  ff14SB has none, so the usual
-// instantiation drops them (8 instructions and 8 registers per torsion).
+// instantiation drops them.
 template <bool GRAD, bool SG>
-__device__ __forceinline__ void torsion_term(const float4* sc, float4* slots, const TorsRec& r, float w, float& e) {
-    const uint32_t i = r.ij & 0x7fffu, j = r.ij >> 16, k = r.kl & 0xffffu, l = r.kl >> 16;
-    float3 rj = f3(sc[j]), rk = f3(sc[k]);
-    float3 F = f3(sc[i]) - rj, G = rj - rk, H = f3(sc[l]) - rk;
-    float3 A = cross(F, G), B = cross(H, G);
-    float G2 = dot(G, G);
-    float iG = G2 > 0.f ? rsqrt_nr(G2) : (G2 == 0.f ? 0.f : G2);   // coincident j,k: |G| = 0, phi = atan2(0,0) = 0 like the reference
-    float Gn = G2 * iG;
-    float X = dot(A, B), Y = -Gn * dot(B, F);
-    float rho2 = fmaf(X, X, Y * Y);
-    float irho = rsqrt_nr(rho2);
-    // atan2(0,0) = 0 in the reference's forward; NaN/inf fall through and propagate
-    float c1 = rho2 == 0.f ? 1.f : X * irho, s1 = rho2 == 0.f ? 0.f : Y * irho;
-    float cn = c1, sn = s1;
-    float en = r.c0, de = 0.f;  // de = dE/dphi
+__device__ __forceinline__ void item_term(const float4* sc, float4* slots, const ItemRec& r, const float4& sg, uint32_t f,
+                                          float wb, float wa, float wt, float& eb, float& ea, float& et) {
+    const uint32_t i = r.ij & 0xffffu, j = r.ij >> 16, k = r.kl & 0xffffu, l = r.kl >> 16;
+    const float3 rj = f3(sc[j]), rk = f3(sc[k]);
+    const float3 F = f3(sc[i]) - rj, G = rj - rk;
+    const float F2 = dot(F, F), G2 = dot(G, G), FG = dot(F, G);
+    const float3 A = cross(F, G);
+    const float A2 = dot(A, A);
+    float3 gi = make_float3(0.f, 0.f, 0.f), gj = gi, gk = gi, gl = gi;
+
+    if (f & IT_T) {
+        const float3 H = f3(sc[l]) - rk;
+        const float3 B = cross(H, G);
+        float iG = G2 > 0.f ? rsqrt_nr(G2) : (G2 == 0.f ? 0.f : G2);   // coincident j,k: |G| = 0, phi = atan2(0,0) = 0 like the reference
+        float Gn = G2 * iG;
+        float X = dot(A, B), Y = -Gn * dot(B, F);
+        float rho2 = fmaf(X, X, Y * Y);
+        float irho = rsqrt_nr(rho2);
+        // atan2(0,0) = 0 in the reference's forward; NaN/inf fall through and propagate
+        float c1 = rho2 == 0.f ? 1.f : X * irho, s1 = rho2 == 0.f ? 0.f : Y * irho;
+        float cn = c1, sn = s1;
+        float en = r.c0, de = 0.f;  // de = dE/dphi
+        const float sgv[NF] = {sg.x, sg.y, sg.z, sg.w};
 #pragma unroll
-    for (int n = 1; n <= NF; ++n) {
-        if (SG) {
-            en = fmaf(r.cg[n - 1], cn, fmaf(r.sg[n - 1], sn, en));
-            if (GRAD) de = fmaf((float)n, fmaf(r.sg[n - 1], cn, -r.cg[n - 1] * sn), de);
-        } else {
-            en = fmaf(r.cg[n - 1], cn, en);
-            if (GRAD) de = fmaf(-(float)n * r.cg[n - 1], sn, de);
+        for (int n = 1; n <= NF; ++n) {
+            if (SG) {
+                en = fmaf(r.cg[n - 1], cn, fmaf(sgv[n - 1], sn, en));
+                if (GRAD) de = fmaf((float)n, fmaf(sgv[n - 1], cn, -r.cg[n - 1] * sn), de);
+            } else {
+                en = fmaf(r.cg[n - 1], cn, en);
+                if (GRAD) de = fmaf(-(float)n * r.cg[n - 1], sn, de);
+            }
+            if (n < NF) {
+                float c2 = fmaf(cn, c1, -sn * s1);
+                sn = fmaf(sn, c1, cn * s1);
+                cn = c2;
+            }
         }
-        if (n < NF) {
-            float c2 = fmaf(cn, c1, -sn * s1);
-            sn = fmaf(sn, c1, cn * s1);
-            cn = c2;
+        if (f & IT_OWN_T) et += en;
+        if (GRAD) {
+            de *= wt;
+            float iA2 = rcp_fast(A2), iB2 = rcp_fast(dot(B, B));
+            float3 ti = (-de * Gn * iA2) * A;
+            float3 tl = (de * Gn * iB2) * B;
+            float fa = de * FG * iA2 * iG, hb = de * dot(H, G) * iB2 * iG;
+            float3 sv = fa * A - hb * B;
+            gi = ti; gl = tl; gj = sv - ti; gk = -1.f * (tl + sv);
         }
     }
-    if (r.ij & OWNER) e += en;
+    if (f & IT_A) {
+        // v1 = ri - rj = F, v2 = rk - rj = -G, n = v1 x v2 = -A
+        float c = -FG * rsqrt_nr(F2 * G2);
+        float cc = fminf(fmaxf(c, -CLAMP), CLAMP);
+        float th = acosf(cc);
+        if (c != c) th = c;  // NaN propagates (fminf/fmaxf would swallow it)
+        float dt = th - r.th0;
+        float kdt = r.ka * dt;
+        if (f & IT_OWN_A) ea = fmaf(kdt, dt, ea);
+        if (GRAD) {
+            // dtheta/dv1 = v1 x (v1 x v2) / (|v1|^2 |v1 x v2|), dtheta/dv2 = -v2 x (v1 x v2) / (|v2|^2 |v1 x v2|):
+            // the cross-product form of -1/sqrt(1-c^2) * dc/dv, which does not cancel near c = +-1.
+            // torch.clamp passes no gradient outside the clamp, so the term is dropped there.
+            float coef = (c > -CLAMP && c < CLAMP) ? 2.f * wa * kdt * rsqrt_fast(A2) : 0.f;
+            if (c != c) coef = c;
+            float3 ai = (-coef * rcp_fast(F2)) * cross(F, A);
+            float3 ak = (-coef * rcp_fast(G2)) * cross(G, A);
+            gi = gi + ai; gk = gk + ak; gj = gj - (ai + ak);
+        }
+    }
+    if (f & IT_B) {
+        const bool jk = f & IT_B_JK;                 // bond (j,k) instead of (i,j)
+        const float3 v = jk ? G : F;
+        const float d2 = jk ? G2 : F2;
+        float inv = d2 > 0.f ? rsqrt_nr(d2) : 0.f;   // autograd: d|v|/dv = 0 at v = 0
+        float d = d2 * inv;
+        d = d2 != d2 ? d2 : d;
+        float dl = d - r.r0;
+        float kdl = r.kb * dl;
+        if (f & IT_OWN_B) eb = fmaf(kdl, dl, eb);
+        if (GRAD) {
+            float3 g = (2.f * wb * kdl * inv) * v;
+            if (jk) { gj = gj + g; gk = gk - g; } else { gi = gi + g; gj = gj - g; }
+        }
+    }
     if (GRAD) {
-        de *= w;
-        float iA2 = rcp_fast(dot(A, A)), iB2 = rcp_fast(dot(B, B));
-        float3 gi = (-de * Gn * iA2) * A;
-        float3 gl = (de * Gn * iB2) * B;
-        float fa = de * dot(F, G) * iA2 * iG, hb = de * dot(H, G) * iB2 * iG;
-        float3 sv = fa * A - hb * B;
         slots[r.s_ij & 0xffffu] = f4(gi);
+        slots[r.s_ij >> 16] = f4(gj);
+        slots[r.s_kl & 0xffffu] = f4(gk);
         slots[r.s_kl >> 16] = f4(gl);
-        slots[r.s_ij >> 16] = f4(sv - gi);
-        slots[r.s_kl & 0xffffu] = f4(-1.f * (gl + sv));
     }
 }
 
 template <bool GRAD, bool SG>
 __global__ void __launch_bounds__(BT, BONDED_MINB)
-bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, const BondRec* __restrict__ bonds,
-              const AngleRec* __restrict__ angles, const TorsRec* __restrict__ tors, const int* __restrict__ cnts,
+bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, const ItemRec* __restrict__ items,
+              const float4* __restrict__ sgs, const int* __restrict__ cnts,
               const float* __restrict__ x, long sxb, int sxc, int sxn,
               float* __restrict__ grad, long sgb, int sgc, int sgn,
               const float* __restrict__ weights, float* __restrict__ e_part /* [B][n_tiles][3] or null */,
@@ -293,20 +306,26 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
     const BTile t = tiles[blockIdx.x];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // term records -> registers, once per CTA (lists are padded to whole warps with inert terms).
-    // 32-term unit u of a list goes to warp (u + off) % 8, register slot u / 8; the angle and torsion
-    // lists start on different warps so that their second-round units do not pile up on warps 0..3.
-    BondRec rb[RB];
-    AngleRec ra[RA];
-    TorsRec rt[RT];
-    bool ab[RB], aa[RA], at[RT];   // warp-uniform activity flags
+    // item records -> registers, once per CTA (the list is padded to whole warps with inert items).
+    // 32-item unit u goes to warp u % NW, register slot u / NW.
+    ItemRec ri[RI];
+    float4 rs[RI];
+    bool ai[RI];                   // warp-uniform activity flags
     constexpr int NW = BT / 32;
+    // terms switched off by term_mask lose their flag bits (the item still writes its four slots)
+    const uint32_t fmask = ((term_mask & MLP_TERM_TORSION) ? (IT_T | IT_OWN_T) : 0u) | ((term_mask & MLP_TERM_ANGLE) ? (IT_A | IT_OWN_A) : 0u) |
+                           ((term_mask & MLP_TERM_BOND) ? (IT_B | IT_B_JK | IT_OWN_B) : 0u);
 #pragma unroll
-    for (int r = 0; r < RB; ++r) { int i0 = (r * NW + warp) * 32; ab[r] = i0 < t.n_bond; if (ab[r]) rb[r] = bonds[t.bond_off + i0 + lane]; }
-#pragma unroll
-    for (int r = 0; r < RA; ++r) { int i0 = (r * NW + warp) * 32; aa[r] = i0 < t.n_angle; if (aa[r]) ra[r] = angles[t.angle_off + i0 + lane]; }
-#pragma unroll
-    for (int r = 0; r < RT; ++r) { int i0 = (r * NW + ((warp - NW / 2) & (NW - 1))) * 32; at[r] = i0 < t.n_tors; if (at[r]) rt[r] = tors[t.tors_off + i0 + lane]; }
+    for (int r = 0; r < RI; ++r) {
+        int i0 = (r * NW + warp) * 32;
+        ai[r] = i0 < t.n_item;
+        rs[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ai[r]) {
+            ri[r] = items[t.item_off + i0 + lane];
+            ri[r].flags &= fmask;
+            if (SG) rs[r] = sgs[t.item_off + i0 + lane];
+        }
+    }
     const int my_cnt = (GRAD && tid < t.n_own) ? cnts[t.cnt_off + tid] : 0;
     const int wcnt = (__reduce_max_sync(0xffffffffu, my_cnt) + 3) & ~3;   // <= max_cnt (a multiple of 4)
     if (GRAD) {
@@ -367,24 +386,13 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
         // stage coordinates (the previous iteration's term phase is over: everybody passed its second barrier)
 #pragma unroll
         for (int q = 0; q < PF; ++q) if (sidx[q] >= 0) scf[sidx[q]] = pf[q];
-        if (GRAD && term_mask != MLP_TERM_BONDED)
-            for (int s = tid; s < max_cnt * STRIDE; s += BT) slots[s] = make_float4(0.f, 0.f, 0.f, 0.f);  // rare: a term type is off
         __syncthreads();
         if (b + 1 < b1) prefetch(xb + sxb);
 
         float eb = 0.f, ea = 0.f, et = 0.f;
-        if (do_b) {
 #pragma unroll
-            for (int r = 0; r < RB; ++r) if (ab[r]) bond_term<GRAD>(sc, slots, rb[r], wb, eb);
-        }
-        if (do_a) {
-#pragma unroll
-            for (int r = 0; r < RA; ++r) if (aa[r]) angle_term<GRAD>(sc, slots, ra[r], wa, ea);
-        }
-        if (do_t) {
-#pragma unroll
-            for (int r = 0; r < RT; ++r) if (at[r]) torsion_term<GRAD, SG>(sc, slots, rt[r], wt, et);
-        }
+        for (int r = 0; r < RI; ++r)
+            if (ai[r]) item_term<GRAD, SG>(sc, slots, ri[r], rs[r], ri[r].flags, wb, wa, wt, eb, ea, et);
         if (e_part) { s_e[0][tid] = eb; s_e[1][tid] = ea; s_e[2][tid] = et; }
         __syncthreads();
         if (e_part && warp < 3) {
@@ -1168,149 +1176,219 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
         for (int n = 0; n < NF; ++n) { t_coef[k][1 + n] = (float)cg[n]; t_coef[k][1 + NF + n] = (float)sg[n]; }
     }
 
-    // per-atom incident (term, role) lists: bonds, then angles, then torsions with a non-zero series
-    struct Inc { int type, idx, role; };
-    std::vector<std::vector<Inc>> inc(N);
-    auto touch = [&](int type, int idx, const int32_t* a, int n) {
-        for (int r = 0; r < n; ++r) inc[a[r]].push_back({type, idx, r});
-    };
-    for (int k = 0; k < nb; ++k) touch(0, k, &T.bonds[2 * k], 2);
-    for (int k = 0; k < na; ++k) touch(1, k, &T.angles[3 * k], 3);
-    for (int k = 0; k < nt; ++k) if (t_live[k]) touch(2, k, &T.torsions[4 * k], 4);
-    int max_cnt = 1;
-    for (int a = 0; a < N; ++a) max_cnt = std::max(max_cnt, (int)inc[a].size());
-    max_cnt = (max_cnt + 3) & ~3;   // the gather reads whole groups of 4 slots
+    if (const char* env = std::getenv("MLP_FORCE_TORSION_SINES")) if (std::atoi(env)) E->torsion_sines = true;  // test hook
     const int stride = SLOT_STRIDE;  // the kernel's compile-time slot stride
+
+    // terms incident to each atom
+    std::vector<std::vector<int>> inc_b(N), inc_a(N), inc_t(N);
+    for (int k = 0; k < nb; ++k) for (int r = 0; r < 2; ++r) inc_b[T.bonds[2 * k + r]].push_back(k);
+    for (int k = 0; k < na; ++k) for (int r = 0; r < 3; ++r) inc_a[T.angles[3 * k + r]].push_back(k);
+    for (int k = 0; k < nt; ++k) if (t_live[k]) for (int r = 0; r < 4; ++r) inc_t[T.torsions[4 * k + r]].push_back(k);
+
+    // A work item: atoms (i,j,k,l) and the ids of the torsion / angle / bond it carries (-1: none).
+    struct Item { int a[4]; int tors, angle, bond; bool bond_jk; };
+    struct TileItems { int a0, n_own; std::vector<Item> items; std::vector<int> halo; std::vector<int> cnt; };
+    std::vector<TileItems> TI;
+    auto uniq = [](std::vector<int>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
+    auto key2 = [](int a, int b) { return std::make_pair(std::min(a, b), std::max(a, b)); };
+    int max_cnt = 1;
+    for (int a0 = 0; a0 < N; a0 += tile_atoms) {
+        TileItems ti;
+        ti.a0 = a0; ti.n_own = std::min(tile_atoms, N - a0);
+        std::vector<int> tb, ta, tt;   // the tile's terms: every term that touches an owned atom
+        for (int a = a0; a < a0 + ti.n_own; ++a) {
+            tb.insert(tb.end(), inc_b[a].begin(), inc_b[a].end());
+            ta.insert(ta.end(), inc_a[a].begin(), inc_a[a].end());
+            tt.insert(tt.end(), inc_t[a].begin(), inc_t[a].end());
+        }
+        uniq(tb); uniq(ta); uniq(tt);
+
+        // ---- angles -> torsions that contain them as (b1,b2,b3) or (b2,b3,b4): maximum bipartite matching (Kuhn)
+        std::map<std::array<int, 3>, int> angle_at;   // (min end, centre, max end) -> index into ta
+        for (size_t q = 0; q < ta.size(); ++q) {
+            const int32_t* a = &T.angles[3 * ta[q]];
+            angle_at[{std::min(a[0], a[2]), a[1], std::max(a[0], a[2])}] = (int)q;
+        }
+        std::vector<std::vector<int>> cand_a(ta.size());          // angle -> candidate torsions (indices into tt)
+        for (size_t q = 0; q < tt.size(); ++q) {
+            const int32_t* b = &T.torsions[4 * tt[q]];
+            for (int side = 0; side < 2; ++side) {
+                const int e0 = b[side], c = b[side + 1], e1 = b[side + 2];
+                auto it = angle_at.find({std::min(e0, e1), c, std::max(e0, e1)});
+                if (it != angle_at.end()) cand_a[it->second].push_back((int)q);
+            }
+        }
+        std::vector<int> tors_angle(tt.size(), -1), angle_tors(ta.size(), -1);
+        {
+            std::vector<char> seen;
+            std::function<bool(int)> grow = [&](int qa) -> bool {
+                for (int qt : cand_a[qa]) {
+                    if (seen[qt]) continue;
+                    seen[qt] = 1;
+                    if (tors_angle[qt] < 0 || grow(tors_angle[qt])) { tors_angle[qt] = qa; angle_tors[qa] = qt; return true; }
+                }
+                return false;
+            };
+            for (size_t qa = 0; qa < ta.size(); ++qa) { seen.assign(tt.size(), 0); grow((int)qa); }
+        }
+        // ---- items: torsions (oriented so that the carried angle is (i,j,k)), then the unmatched angles
+        auto& items = ti.items;
+        for (size_t q = 0; q < tt.size(); ++q) {
+            const int32_t* b = &T.torsions[4 * tt[q]];
+            Item it{{b[0], b[1], b[2], b[3]}, tt[q], -1, -1, false};
+            if (tors_angle[q] >= 0) {
+                it.angle = ta[tors_angle[q]];
+                if (T.angles[3 * it.angle + 1] != b[1]) { it.a[0] = b[3]; it.a[1] = b[2]; it.a[2] = b[1]; it.a[3] = b[0]; }  // centre is b3: reverse
+            }
+            items.push_back(it);
+        }
+        for (size_t q = 0; q < ta.size(); ++q)
+            if (angle_tors[q] < 0) {
+                const int32_t* a = &T.angles[3 * ta[q]];
+                items.push_back(Item{{a[0], a[1], a[2], a[0]}, -1, ta[q], -1, false});   // l: dummy (= i)
+            }
+        // ---- bonds -> items that contain them as (i,j) or (j,k) ((k,l) too for a torsion without angle: it can be reversed)
+        std::map<std::pair<int, int>, int> bond_at;
+        for (size_t q = 0; q < tb.size(); ++q) bond_at[key2(T.bonds[2 * tb[q]], T.bonds[2 * tb[q] + 1])] = (int)q;
+        std::vector<std::vector<std::pair<int, int>>> cand_b(tb.size());   // bond -> (item, position 0: ij, 1: jk, 2: kl)
+        for (size_t q = 0; q < items.size(); ++q) {
+            const Item& it = items[q];
+            const int npos = it.tors >= 0 ? (it.angle >= 0 ? 2 : 3) : 2;
+            for (int pos = 0; pos < npos; ++pos) {
+                auto f = bond_at.find(key2(it.a[pos], it.a[pos + 1]));
+                if (f != bond_at.end()) cand_b[f->second].push_back({(int)q, pos});
+            }
+        }
+        std::vector<int> item_bond(items.size(), -1), item_pos(items.size(), 0), bond_item(tb.size(), -1);
+        {
+            std::vector<char> seen;
+            std::function<bool(int)> grow = [&](int qb) -> bool {
+                for (auto& c : cand_b[qb]) {
+                    if (seen[c.first]) continue;
+                    seen[c.first] = 1;
+                    if (item_bond[c.first] < 0 || grow(item_bond[c.first])) { item_bond[c.first] = qb; item_pos[c.first] = c.second; bond_item[qb] = c.first; return true; }
+                }
+                return false;
+            };
+            for (size_t qb = 0; qb < tb.size(); ++qb) { seen.assign(items.size(), 0); grow((int)qb); }
+        }
+        for (size_t q = 0; q < items.size(); ++q)
+            if (item_bond[q] >= 0) {
+                Item& it = items[q];
+                it.bond = tb[item_bond[q]];
+                if (item_pos[q] == 2) { std::swap(it.a[0], it.a[3]); std::swap(it.a[1], it.a[2]); it.bond_jk = false; }   // (k,l) -> reversed (i,j)
+                else it.bond_jk = item_pos[q] == 1;
+            }
+        for (size_t q = 0; q < tb.size(); ++q)
+            if (bond_item[q] < 0) {
+                const int32_t* b = &T.bonds[2 * tb[q]];
+                items.push_back(Item{{b[0], b[1], b[0], b[0]}, -1, -1, tb[q], false});   // k, l: dummies
+            }
+        // warps should be uniform in what their items carry
+        auto kind = [](const Item& it) { return (it.tors >= 0 ? 0 : 4) + (it.angle >= 0 ? 0 : 2) + (it.bond >= 0 ? 0 : 1); };
+        std::stable_sort(items.begin(), items.end(), [&](const Item& x, const Item& y) { return kind(x) < kind(y); });
+        if (((items.size() + 31) & ~(size_t)31) > (size_t)RI * BT) return 1;
+
+        // halo atoms and per-atom contribution counts (one slot per item that touches the atom with a real role)
+        for (const Item& it : items) for (int r = 0; r < 4; ++r) if (it.a[r] < a0 || it.a[r] >= a0 + ti.n_own) ti.halo.push_back(it.a[r]);
+        uniq(ti.halo);
+        const int n_at = ti.n_own + (int)ti.halo.size();
+        if (3 * n_at > PF * BT || n_at >= 0xffff) return 1;
+        ti.cnt.assign(ti.n_own, 0);
+        for (const Item& it : items) {
+            const int roles = it.tors >= 0 ? 4 : it.angle >= 0 ? 3 : 2;
+            for (int r = 0; r < roles; ++r) if (it.a[r] >= a0 && it.a[r] < a0 + ti.n_own) max_cnt = std::max(max_cnt, ++ti.cnt[it.a[r] - a0]);
+        }
+        TI.push_back(std::move(ti));
+    }
+    max_cnt = (max_cnt + 3) & ~3;   // the gather reads whole groups of 4 slots
     if ((size_t)max_cnt * stride + 1 >= 0xffff) return 1;
     const uint32_t dump = (uint32_t)(max_cnt * stride);
 
-    if (const char* env = std::getenv("MLP_FORCE_TORSION_SINES")) if (std::atoi(env)) E->torsion_sines = true;  // test hook
     std::vector<BTile> tiles;
     std::vector<int> halo_all, cnt_all;
-    std::vector<BondRec> bonds_all;
-    std::vector<AngleRec> angles_all;
-    std::vector<TorsRec> tors_all;
+    std::vector<ItemRec> items_all;
+    std::vector<float4> sg_all;
     int max_atoms = 1;
-    for (int a0 = 0; a0 < N; a0 += tile_atoms) {
-        const int n_own = std::min(tile_atoms, N - a0);
+    size_t n_items_real = 0;
+    for (TileItems& ti : TI) {
+        const int a0 = ti.a0, n_own = ti.n_own;
+        const int n_at = n_own + (int)ti.halo.size();
         BTile bt{};
         bt.a0 = a0; bt.n_own = n_own;
-        std::vector<int> tb, ta, tt;
-        for (int a = a0; a < a0 + n_own; ++a)
-            for (const Inc& tm : inc[a]) (tm.type == 0 ? tb : tm.type == 1 ? ta : tt).push_back(tm.idx);
-        auto uniq = [](std::vector<int>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
-        uniq(tb); uniq(ta); uniq(tt);
-        auto pad32 = [](size_t n) { return (int)((n + 31) & ~(size_t)31); };
-        if (pad32(tb.size()) > RB * BT || pad32(ta.size()) > RA * BT || pad32(tt.size()) > RT * BT) return 1;
-        std::vector<int> halo;
-        auto need = [&](int a) { if (a < a0 || a >= a0 + n_own) halo.push_back(a); };
-        for (int k : tb) for (int r = 0; r < 2; ++r) need(T.bonds[2 * k + r]);
-        for (int k : ta) for (int r = 0; r < 3; ++r) need(T.angles[3 * k + r]);
-        for (int k : tt) for (int r = 0; r < 4; ++r) need(T.torsions[4 * k + r]);
-        uniq(halo);
-        const int n_at = n_own + (int)halo.size();
-        if (3 * n_at > PF * BT || n_at >= 0x7fff) return 1;
+        auto own = [&](int a) { return a >= a0 && a < a0 + n_own; };
         auto local = [&](int a) -> uint32_t {
-            if (a >= a0 && a < a0 + n_own) return (uint32_t)(a - a0);
-            return (uint32_t)(n_own + (std::lower_bound(halo.begin(), halo.end(), a) - halo.begin()));
+            if (own(a)) return (uint32_t)(a - a0);
+            return (uint32_t)(n_own + (std::lower_bound(ti.halo.begin(), ti.halo.end(), a) - ti.halo.begin()));
         };
-        // slot of (own atom la, its k-th incident role) = k*stride + la; roles on halo atoms go to the dump slot
-        std::map<std::array<int, 3>, uint32_t> slot_of;
+        // slot of (own atom la, its k-th contribution) = k*stride + la; roles on halo atoms and dummy roles go to the dump slot
+        std::vector<int> next(n_own, 0);
+        bt.item_off = (int)items_all.size();
         bt.cnt_off = (int)cnt_all.size();
+        for (const Item& it : ti.items) {
+            ItemRec r{};
+            const int roles = it.tors >= 0 ? 4 : it.angle >= 0 ? 3 : 2;
+            uint32_t la[4], sl[4];
+            for (int q = 0; q < 4; ++q) {
+                la[q] = local(it.a[q]);
+                sl[q] = (q < roles && own(it.a[q])) ? (uint32_t)(next[it.a[q] - a0]++ * stride + (it.a[q] - a0)) : dump;
+            }
+            r.ij = la[0] | (la[1] << 16); r.kl = la[2] | (la[3] << 16);
+            r.s_ij = sl[0] | (sl[1] << 16); r.s_kl = sl[2] | (sl[3] << 16);
+            float4 sg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it.tors >= 0) {
+                r.flags |= IT_T | (own(T.torsions[4 * it.tors]) ? IT_OWN_T : 0u);
+                r.c0 = t_coef[it.tors][0];
+                for (int n = 0; n < NF; ++n) r.cg[n] = t_coef[it.tors][1 + n];
+                sg = make_float4(t_coef[it.tors][1 + NF], t_coef[it.tors][2 + NF], t_coef[it.tors][3 + NF], t_coef[it.tors][4 + NF]);
+            }
+            if (it.angle >= 0) {
+                r.flags |= IT_A | (own(T.angles[3 * it.angle]) ? IT_OWN_A : 0u);
+                r.th0 = (float)T.angle_para[2 * it.angle]; r.ka = (float)T.angle_para[2 * it.angle + 1];
+            }
+            if (it.bond >= 0) {
+                r.flags |= IT_B | (it.bond_jk ? IT_B_JK : 0u) | (own(T.bonds[2 * it.bond]) ? IT_OWN_B : 0u);
+                r.r0 = (float)T.bond_para[2 * it.bond]; r.kb = (float)T.bond_para[2 * it.bond + 1];
+            }
+            items_all.push_back(r);
+            sg_all.push_back(sg);
+            ++n_items_real;
+        }
+        while ((items_all.size() - bt.item_off) % 32) {      // inert items: no term, four stores to the dump slot
+            ItemRec r{};
+            r.s_ij = dump | (dump << 16); r.s_kl = dump | (dump << 16);
+            items_all.push_back(r);
+            sg_all.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        bt.n_item = (int)items_all.size() - bt.item_off;
         for (int la = 0; la < n_own; ++la) {
-            const auto& v = inc[a0 + la];
-            for (size_t k = 0; k < v.size(); ++k) slot_of[{v[k].type, v[k].idx, v[k].role}] = (uint32_t)(k * stride + la);
-            cnt_all.push_back((int)v.size());
+            if (next[la] != ti.cnt[la]) { mlp_set_error("pack_bonded: internal error, slot count mismatch"); return MLP_E_ARG; }
+            cnt_all.push_back(next[la]);
         }
-        auto slot = [&](int type, int idx, int role) -> uint32_t {
-            auto it = slot_of.find({type, idx, role});
-            return it == slot_of.end() ? dump : it->second;
-        };
-        auto owner = [&](int first_atom) { return (first_atom >= a0 && first_atom < a0 + n_own) ? OWNER : 0u; };
-        const uint32_t l1 = std::min(1, n_at - 1), l2 = std::min(2, n_at - 1), l3 = std::min(3, n_at - 1);
-
-        bt.bond_off = (int)bonds_all.size();
-        for (int k : tb) {
-            BondRec r{};
-            r.ij = local(T.bonds[2 * k]) | owner(T.bonds[2 * k]) | (local(T.bonds[2 * k + 1]) << 16);
-            r.slots = slot(0, k, 0) | (slot(0, k, 1) << 16);
-            r.r0 = (float)T.bond_para[2 * k]; r.k = (float)T.bond_para[2 * k + 1];
-            bonds_all.push_back(r);
-        }
-        while ((bonds_all.size() - bt.bond_off) % 32) bonds_all.push_back(BondRec{0u | (l1 << 16), dump | (dump << 16), 0.f, 0.f});
-        bt.n_bond = (int)bonds_all.size() - bt.bond_off;
-
-        bt.angle_off = (int)angles_all.size();
-        for (int k : ta) {
-            AngleRec r{};
-            r.ij = local(T.angles[3 * k]) | owner(T.angles[3 * k]) | (local(T.angles[3 * k + 1]) << 16);
-            r.k = local(T.angles[3 * k + 2]);
-            r.s_ij = slot(1, k, 0) | (slot(1, k, 1) << 16); r.s_k = slot(1, k, 2);
-            r.th0 = (float)T.angle_para[2 * k]; r.kf = (float)T.angle_para[2 * k + 1];
-            angles_all.push_back(r);
-        }
-        while ((angles_all.size() - bt.angle_off) % 32) {
-            AngleRec r{};
-            r.ij = 0u | (l1 << 16); r.k = l2; r.s_ij = dump | (dump << 16); r.s_k = dump;
-            angles_all.push_back(r);
-        }
-        bt.n_angle = (int)angles_all.size() - bt.angle_off;
-
-        bt.tors_off = (int)tors_all.size();
-        for (int k : tt) {
-            TorsRec r{};
-            r.ij = local(T.torsions[4 * k]) | owner(T.torsions[4 * k]) | (local(T.torsions[4 * k + 1]) << 16);
-            r.kl = local(T.torsions[4 * k + 2]) | (local(T.torsions[4 * k + 3]) << 16);
-            r.s_ij = slot(2, k, 0) | (slot(2, k, 1) << 16); r.s_kl = slot(2, k, 2) | (slot(2, k, 3) << 16);
-            r.c0 = t_coef[k][0];
-            for (int n = 0; n < NF; ++n) { r.cg[n] = t_coef[k][1 + n]; r.sg[n] = t_coef[k][1 + NF + n]; }
-            tors_all.push_back(r);
-        }
-        while ((tors_all.size() - bt.tors_off) % 32) {
-            TorsRec r{};
-            r.ij = 0u | (l1 << 16); r.kl = l2 | (l3 << 16); r.s_ij = dump | (dump << 16); r.s_kl = dump | (dump << 16);
-            tors_all.push_back(r);
-        }
-        bt.n_tors = (int)tors_all.size() - bt.tors_off;
-
         // self-check of the packed records (compute-sanitizer is not available on the target pool): every local
         // atom index addresses a staged atom, every slot id addresses an allocated slot or the dump slot
-        {
-            bool ok = true;
-            auto at_ok = [&](uint32_t la) { return la < (uint32_t)n_at; };
-            auto sl_ok = [&](uint32_t sl) { return sl <= dump; };
-            for (size_t q = bt.bond_off; q < bonds_all.size(); ++q) {
-                const BondRec& r = bonds_all[q];
-                ok = ok && at_ok(r.ij & 0x7fffu) && at_ok(r.ij >> 16) && sl_ok(r.slots & 0xffffu) && sl_ok(r.slots >> 16);
-            }
-            for (size_t q = bt.angle_off; q < angles_all.size(); ++q) {
-                const AngleRec& r = angles_all[q];
-                ok = ok && at_ok(r.ij & 0x7fffu) && at_ok(r.ij >> 16) && at_ok(r.k) && sl_ok(r.s_ij & 0xffffu) && sl_ok(r.s_ij >> 16) && sl_ok(r.s_k);
-            }
-            for (size_t q = bt.tors_off; q < tors_all.size(); ++q) {
-                const TorsRec& r = tors_all[q];
-                ok = ok && at_ok(r.ij & 0x7fffu) && at_ok(r.ij >> 16) && at_ok(r.kl & 0xffffu) && at_ok(r.kl >> 16) &&
-                     sl_ok(r.s_ij & 0xffffu) && sl_ok(r.s_ij >> 16) && sl_ok(r.s_kl & 0xffffu) && sl_ok(r.s_kl >> 16);
-            }
-            if (!ok) { mlp_set_error("pack_bonded: internal error, record index out of range"); return MLP_E_ARG; }
+        for (size_t q = bt.item_off; q < items_all.size(); ++q) {
+            const ItemRec& r = items_all[q];
+            const uint32_t at[4] = {r.ij & 0xffffu, r.ij >> 16, r.kl & 0xffffu, r.kl >> 16};
+            const uint32_t sl[4] = {r.s_ij & 0xffffu, r.s_ij >> 16, r.s_kl & 0xffffu, r.s_kl >> 16};
+            for (int c = 0; c < 4; ++c)
+                if (at[c] >= (uint32_t)n_at || sl[c] > dump) { mlp_set_error("pack_bonded: internal error, record index out of range"); return MLP_E_ARG; }
         }
-        bt.halo_off = (int)halo_all.size(); bt.n_halo = (int)halo.size();
-        halo_all.insert(halo_all.end(), halo.begin(), halo.end());
+        bt.halo_off = (int)halo_all.size(); bt.n_halo = (int)ti.halo.size();
+        halo_all.insert(halo_all.end(), ti.halo.begin(), ti.halo.end());
         max_atoms = std::max(max_atoms, n_at);
         tiles.push_back(bt);
     }
     const size_t smem = ((size_t)max_atoms + (size_t)max_cnt * stride + 1) * sizeof(float4);
     if (smem > 200 * 1024) { mlp_set_error("pack_bonded: too many gradient contributions per atom for the shared-memory slot table"); return MLP_E_ARG; }
-    // (above BONDED_SMEM_CAP fewer CTAs fit per SM; the slot stride is a compile-time constant, so a smaller
-    //  tile would not shrink the table)
     E->n_tiles = (int)tiles.size(); E->tile_atoms = tile_atoms; E->max_cnt = max_cnt;
-    E->max_atoms = max_atoms; E->bonded_smem = smem;
+    E->max_atoms = max_atoms; E->bonded_smem = smem; E->n_items = (long)n_items_real;
     int rc;
     if ((rc = upload(E, &E->d_tiles, tiles))) return rc;
     if ((rc = upload(E, &E->d_halo, halo_all))) return rc;
-    if ((rc = upload(E, &E->d_bonds, bonds_all))) return rc;
-    if ((rc = upload(E, &E->d_angles, angles_all))) return rc;
-    if ((rc = upload(E, &E->d_tors, tors_all))) return rc;
+    if ((rc = upload(E, &E->d_items, items_all))) return rc;
+    if (!E->torsion_sines) sg_all.assign(1, make_float4(0.f, 0.f, 0.f, 0.f));
+    if ((rc = upload(E, &E->d_sg, sg_all))) return rc;
     if ((rc = upload(E, &E->d_cnt, cnt_all))) return rc;
     return MLP_OK;
 }
@@ -1448,7 +1526,7 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
     cudaDeviceGetAttribute(&E->sm_count, cudaDevAttrMultiProcessorCount, device);
     int rc = MLP_OK;
     int tile = BT;
-    if (const char* env = std::getenv("MLP_BONDED_TILE")) tile = std::max(32, std::min(BT, std::atoi(env) & ~31));
+    if (const char* env = std::getenv("MLP_BONDED_TILE")) tile = std::max(32, std::min(BT, std::atoi(env) & ~7));
     while (true) {
         rc = pack_bonded(E, *t, tile);
         if (rc == 1 && tile > 32) { tile -= 32; for (void* p : E->allocs) cudaFree(p); E->allocs.clear(); continue; }
@@ -1585,7 +1663,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         prof_begin(1);
         int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
         dim3 grid(e->n_tiles, (unsigned)((B + cpc - 1) / cpc));
-#define BONDED_LAUNCH(G, S) bonded_kernel<G, S><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_bonds, e->d_angles, e->d_tors, e->d_cnt, \
+#define BONDED_LAUNCH(G, S) bonded_kernel<G, S><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_items, e->d_sg, e->d_cnt, \
             x, sxb, (int)sxc, (int)sxn, grad, sgb, (int)sgc, (int)sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc, \
             term_mask & MLP_TERM_BONDED, grad ? (int)accumulate : 0, e->max_atoms, e->max_cnt)
         if (grad) { if (e->torsion_sines) BONDED_LAUNCH(true, true); else BONDED_LAUNCH(true, false); }
