@@ -8,14 +8,15 @@
 // output is produced by a fixed-order sum, so results are bit-reproducible run to run.
 //
 // Bonded kernel
-//   CTA = (atom tile, chunk of conformations).  The tile's term records live in REGISTERS for
-//   the whole chunk, so topology is read once per CTA, not once per conformation.  Per
-//   conformation: coordinates of the tile (+halo) are staged in shared memory as float4, each
-//   thread evaluates its terms and writes every role's gradient to a private shared-memory slot;
-//   slot (atom a, k-th contribution) lives at [k*stride + a], so the term phase writes and the
-//   per-atom gather reads are both bank-conflict-free for neighbouring atoms; one thread per atom
-//   sums its column and writes the gradient once.  Terms that straddle a tile boundary are
-//   evaluated by both tiles (energy counted by the owner of role 0).
+//   CTA = (atom tile, chunk of conformations).  The host matches every angle to a torsion that contains it and
+//   every bond to an item that contains it, so a WORK ITEM is up to one torsion + one angle + one bond on the same
+//   four atoms: four coordinate reads, shared difference vectors / cross product, one summed gradient per atom.
+//   The tile's item records live in REGISTERS for the whole chunk (topology is read once per CTA, not once per
+//   conformation).  Per conformation: coordinates of the tile (+halo) are staged in shared memory as float4, each
+//   thread evaluates its items (branch-free) and writes every atom's gradient to a private shared-memory slot;
+//   slot (atom a, k-th contribution) lives at [k*stride + a]; one thread per atom sums its column and writes the
+//   gradient once.  Items that straddle a tile boundary are evaluated by both tiles (energy counted by the tile
+//   that owns the term's first atom).
 //
 // Non-bonded kernel
 //   Work item = (conformation, 128x128 atom tile pair J>=I), one one-warp CTA each, tile pairs ordered
@@ -196,20 +197,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 //          evaluated as a Fourier series in (cos phi, sin phi) - no atan2 / cos calls.
 // SG: the series has sine coefficients (phases other than 0 / pi).  ff14SB has none, so the usual
 // instantiation drops them.
+// Branch-free form: every item evaluates all three terms in ONE basic block, so the scheduler can interleave the
+// three dependency chains (the kernel is latency-bound).  Terms an item does not carry have zero force constants /
+// Fourier coefficients; the few reciprocals that could turn 0 * inf into NaN on an item's dummy atoms are forced
+// to zero instead (hT / hA selects), and energies are added under the OWN flags, which imply presence.
 template <bool GRAD, bool SG>
 __device__ __forceinline__ void item_term(const float4* sc, float4* slots, const ItemRec& r, const float4& sg, uint32_t f,
                                           float wb, float wa, float wt, float& eb, float& ea, float& et) {
     const uint32_t i = r.ij & 0xffffu, j = r.ij >> 16, k = r.kl & 0xffffu, l = r.kl >> 16;
+    const bool hT = f & IT_T, hA = f & IT_A;
     const float3 rj = f3(sc[j]), rk = f3(sc[k]);
-    const float3 F = f3(sc[i]) - rj, G = rj - rk;
+    const float3 F = f3(sc[i]) - rj, G = rj - rk, H = f3(sc[l]) - rk;
     const float F2 = dot(F, F), G2 = dot(G, G), FG = dot(F, G);
-    const float3 A = cross(F, G);
+    const float3 A = cross(F, G), B = cross(H, G);
     const float A2 = dot(A, A);
-    float3 gi = make_float3(0.f, 0.f, 0.f), gj = gi, gk = gi, gl = gi;
-
-    if (f & IT_T) {
-        const float3 H = f3(sc[l]) - rk;
-        const float3 B = cross(H, G);
+    float3 gi, gj, gk, gl;
+    // ---- torsion
+    {
         float iG = G2 > 0.f ? rsqrt_nr(G2) : (G2 == 0.f ? 0.f : G2);   // coincident j,k: |G| = 0, phi = atan2(0,0) = 0 like the reference
         float Gn = G2 * iG;
         float X = dot(A, B), Y = -Gn * dot(B, F);
@@ -235,10 +239,10 @@ __device__ __forceinline__ void item_term(const float4* sc, float4* slots, const
                 cn = c2;
             }
         }
-        if (f & IT_OWN_T) et += en;
+        et += (f & IT_OWN_T) ? en : 0.f;
         if (GRAD) {
-            de *= wt;
-            float iA2 = rcp_fast(A2), iB2 = rcp_fast(dot(B, B));
+            de = hT ? de * wt : 0.f;
+            float iA2 = hT ? rcp_fast(A2) : 0.f, iB2 = hT ? rcp_fast(dot(B, B)) : 0.f;
             float3 ti = (-de * Gn * iA2) * A;
             float3 tl = (de * Gn * iB2) * B;
             float fa = de * FG * iA2 * iG, hb = de * dot(H, G) * iB2 * iG;
@@ -246,28 +250,31 @@ __device__ __forceinline__ void item_term(const float4* sc, float4* slots, const
             gi = ti; gl = tl; gj = sv - ti; gk = -1.f * (tl + sv);
         }
     }
-    if (f & IT_A) {
-        // v1 = ri - rj = F, v2 = rk - rj = -G, n = v1 x v2 = -A
+    // ---- angle (i,j,k): v1 = ri - rj = F, v2 = rk - rj = -G, n = v1 x v2 = -A
+    {
         float c = -FG * rsqrt_nr(F2 * G2);
         float cc = fminf(fmaxf(c, -CLAMP), CLAMP);
         float th = acosf(cc);
         if (c != c) th = c;  // NaN propagates (fminf/fmaxf would swallow it)
         float dt = th - r.th0;
         float kdt = r.ka * dt;
-        if (f & IT_OWN_A) ea = fmaf(kdt, dt, ea);
+        ea += (f & IT_OWN_A) ? kdt * dt : 0.f;
         if (GRAD) {
             // dtheta/dv1 = v1 x (v1 x v2) / (|v1|^2 |v1 x v2|), dtheta/dv2 = -v2 x (v1 x v2) / (|v2|^2 |v1 x v2|):
             // the cross-product form of -1/sqrt(1-c^2) * dc/dv, which does not cancel near c = +-1.
             // torch.clamp passes no gradient outside the clamp, so the term is dropped there.
             float coef = (c > -CLAMP && c < CLAMP) ? 2.f * wa * kdt * rsqrt_fast(A2) : 0.f;
             if (c != c) coef = c;
-            float3 ai = (-coef * rcp_fast(F2)) * cross(F, A);
-            float3 ak = (-coef * rcp_fast(G2)) * cross(G, A);
+            coef = hA ? coef : 0.f;
+            float qi = hA ? -coef * rcp_fast(F2) : 0.f, qk = hA ? -coef * rcp_fast(G2) : 0.f;
+            float3 ai = qi * cross(F, A);
+            float3 ak = qk * cross(G, A);
             gi = gi + ai; gk = gk + ak; gj = gj - (ai + ak);
         }
     }
-    if (f & IT_B) {
-        const bool jk = f & IT_B_JK;                 // bond (j,k) instead of (i,j)
+    // ---- bond (i,j) or (j,k)
+    {
+        const bool jk = f & IT_B_JK;
         const float3 v = jk ? G : F;
         const float d2 = jk ? G2 : F2;
         float inv = d2 > 0.f ? rsqrt_nr(d2) : 0.f;   // autograd: d|v|/dv = 0 at v = 0
@@ -275,10 +282,12 @@ __device__ __forceinline__ void item_term(const float4* sc, float4* slots, const
         d = d2 != d2 ? d2 : d;
         float dl = d - r.r0;
         float kdl = r.kb * dl;
-        if (f & IT_OWN_B) eb = fmaf(kdl, dl, eb);
+        eb += (f & IT_OWN_B) ? kdl * dl : 0.f;
         if (GRAD) {
-            float3 g = (2.f * wb * kdl * inv) * v;
-            if (jk) { gj = gj + g; gk = gk - g; } else { gi = gi + g; gj = gj - g; }
+            float sc2 = (f & IT_B) ? 2.f * wb * kdl * inv : 0.f;
+            float3 g = sc2 * v;
+            float mi = jk ? 0.f : 1.f, mk = jk ? -1.f : 0.f;     // (i,j): +g on i, -g on j; (j,k): +g on j, -g on k
+            gi = gi + mi * g; gk = gk + mk * g; gj = gj - (mi + mk) * g;
         }
     }
     if (GRAD) {
