@@ -109,6 +109,18 @@ void mlp_topology_destroy(mlp_topology* t);
  * Device side.
  */
 
+/* Host-only inspection of the bonded kernel's work plan (no device needed; used by the CPU tests).
+ * The bonded kernel evaluates WORK ITEMS: up to one torsion (i,j,k,l), one angle (i,j,k) and one bond
+ * ((i,j) or (j,k)) on the same four atoms; every tile of `tile_atoms` consecutive atoms gets the
+ * items that touch one of its atoms.  Rows of `items` ([capacity][9] int32):
+ *   tile, i, j, k, l (global atom indices; unused roles repeat i), torsion id | -1, angle id | -1,
+ *   bond id | -1, 1 if the bond sits on (j,k) else 0.
+ * `*n_items` receives the number of rows (call with items = NULL to size the buffer);
+ * stats[0] = tiles, [1] = max gradient contributions per atom, [2] = 1 if a torsion phase needs sine terms,
+ * [3] = live (non-zero) torsions. */
+int mlp_bonded_plan(const mlp_topology* t, int tile_atoms, int64_t* n_items, int32_t* items, int64_t capacity,
+                    int64_t stats[4]);
+
 /* Number of CUDA devices visible (0 if none / no driver).  Never fails. */
 int mlp_device_count(void);
 

@@ -23,6 +23,7 @@ SYMBOLS = {
     "mlp_topology_atoms": (c_int, [c_void_p] + [c_void_p] * 6),
     "mlp_topology_pairs14": (c_int, [c_void_p, c_void_p]),
     "mlp_topology_destroy": (None, [c_void_p]),
+    "mlp_bonded_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "mlp_device_count": (c_int, []),
     "mlp_energy_create": (c_int, [c_void_p, c_int, c_uint32, POINTER(c_void_p)]),
     "mlp_energy_destroy": (None, [c_void_p]),

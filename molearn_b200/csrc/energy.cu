@@ -1151,14 +1151,29 @@ template <class T> int upload(mlp_energy* E, T** dst, const std::vector<T>& v) {
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// A bonded work item: atoms (i,j,k,l) and the ids of the torsion / angle / bond it carries (-1: none).
+struct Item { int a[4]; int tors, angle, bond; bool bond_jk; };
+struct TileItems { int a0, n_own; std::vector<Item> items; std::vector<int> halo; std::vector<int> cnt; };
+struct BondedPlan {
+    std::vector<char> t_live;                                  // torsion has a non-zero series
+    std::vector<std::array<float, 1 + 2 * NF>> t_coef;         // c0, cosine[NF], sine[NF]
+    bool torsion_sines = false;
+    std::vector<TileItems> tiles;
+    int max_cnt = 1;                                           // max gradient contributions per atom (multiple of 4)
+};
+
+// Host-only part of the bonded packing: Fourier coefficients, per-tile work items (angle -> torsion and
+// bond -> item matchings), halo lists, per-atom contribution counts.
 // returns 1 if the tile size does not fit the kernel's static limits (the caller retries smaller)
-int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
+int plan_bonded(const mlp_topology& T, int tile_atoms, BondedPlan& plan) {
     const int N = T.n_atoms;
     const int nb = (int)T.bonds.size() / 2, na = (int)T.angles.size() / 3, nt = (int)T.torsions.size() / 4, P = T.P;
     // torsion Fourier coefficients from the fp32-rounded parameters (the reference moves its
     // tables to the device with .float(), torch_protein_energy.py:123)
-    std::vector<char> t_live(nt, 0);
-    std::vector<std::array<float, 1 + 2 * NF>> t_coef(nt);
+    std::vector<char>& t_live = plan.t_live;
+    std::vector<std::array<float, 1 + 2 * NF>>& t_coef = plan.t_coef;
+    t_live.assign(nt, 0);
+    t_coef.assign(nt, {});
     for (int k = 0; k < nt; ++k) {
         double c0 = 0, cg[NF] = {0}, sg[NF] = {0};
         bool live = false;
@@ -1180,13 +1195,12 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
         }
         t_live[k] = live;
         for (int n = 0; n < NF; ++n)   // sin(fp32(pi)) = -8.7e-8: below 1e-6 of the cosine coefficient it is rounding noise
-            if (std::fabs(sg[n]) > 1e-6 * std::max(std::fabs(cg[n]), 1e-30)) E->torsion_sines = true;
+            if (std::fabs(sg[n]) > 1e-6 * std::max(std::fabs(cg[n]), 1e-30)) plan.torsion_sines = true;
         t_coef[k][0] = (float)c0;
         for (int n = 0; n < NF; ++n) { t_coef[k][1 + n] = (float)cg[n]; t_coef[k][1 + NF + n] = (float)sg[n]; }
     }
 
-    if (const char* env = std::getenv("MLP_FORCE_TORSION_SINES")) if (std::atoi(env)) E->torsion_sines = true;  // test hook
-    const int stride = SLOT_STRIDE;  // the kernel's compile-time slot stride
+    if (const char* env = std::getenv("MLP_FORCE_TORSION_SINES")) if (std::atoi(env)) plan.torsion_sines = true;  // test hook
 
     // terms incident to each atom
     std::vector<std::vector<int>> inc_b(N), inc_a(N), inc_t(N);
@@ -1194,10 +1208,8 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
     for (int k = 0; k < na; ++k) for (int r = 0; r < 3; ++r) inc_a[T.angles[3 * k + r]].push_back(k);
     for (int k = 0; k < nt; ++k) if (t_live[k]) for (int r = 0; r < 4; ++r) inc_t[T.torsions[4 * k + r]].push_back(k);
 
-    // A work item: atoms (i,j,k,l) and the ids of the torsion / angle / bond it carries (-1: none).
-    struct Item { int a[4]; int tors, angle, bond; bool bond_jk; };
-    struct TileItems { int a0, n_own; std::vector<Item> items; std::vector<int> halo; std::vector<int> cnt; };
-    std::vector<TileItems> TI;
+    std::vector<TileItems>& TI = plan.tiles;
+    TI.clear();
     auto uniq = [](std::vector<int>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
     auto key2 = [](int a, int b) { return std::make_pair(std::min(a, b), std::max(a, b)); };
     int max_cnt = 1;
@@ -1311,7 +1323,19 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
         TI.push_back(std::move(ti));
     }
     max_cnt = (max_cnt + 3) & ~3;   // the gather reads whole groups of 4 slots
-    if ((size_t)max_cnt * stride + 1 >= 0xffff) return 1;
+    if ((size_t)max_cnt * SLOT_STRIDE + 1 >= 0xffff) return 1;
+    plan.max_cnt = max_cnt;
+    return MLP_OK;
+}
+
+int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
+    BondedPlan plan;
+    if (int rc = plan_bonded(T, tile_atoms, plan)) return rc;
+    E->torsion_sines = plan.torsion_sines;
+    const auto& t_coef = plan.t_coef;
+    std::vector<TileItems>& TI = plan.tiles;
+    const int max_cnt = plan.max_cnt;
+    const int stride = SLOT_STRIDE;  // the kernel's compile-time slot stride
     const uint32_t dump = (uint32_t)(max_cnt * stride);
 
     std::vector<BTile> tiles;
@@ -1513,6 +1537,32 @@ Workspace layout(const mlp_energy* e, int64_t B, uint32_t term_mask, bool grad) 
 // C ABI
 // ------------------------------------------------------------------------------------------
 extern "C" {
+
+int mlp_bonded_plan(const mlp_topology* t, int tile_atoms, int64_t* n_items, int32_t* items, int64_t capacity, int64_t stats[4]) {
+    if (!t || !n_items || tile_atoms < 1 || tile_atoms > BT) { mlp_set_error("mlp_bonded_plan: bad argument"); return MLP_E_ARG; }
+    BondedPlan plan;
+    int rc = plan_bonded(*t, tile_atoms, plan);
+    if (rc == 1) { mlp_set_error("mlp_bonded_plan: topology too dense for this tile size"); return MLP_E_ARG; }
+    if (rc) return rc;
+    int64_t n = 0;
+    for (size_t ti = 0; ti < plan.tiles.size(); ++ti)
+        for (const Item& it : plan.tiles[ti].items) {
+            if (items && n < capacity) {
+                int32_t* row = items + 9 * n;
+                row[0] = (int32_t)ti;
+                for (int q = 0; q < 4; ++q) row[1 + q] = it.a[q];
+                row[5] = it.tors; row[6] = it.angle; row[7] = it.bond; row[8] = it.bond_jk ? 1 : 0;
+            }
+            ++n;
+        }
+    *n_items = n;
+    if (stats) {
+        stats[0] = (int64_t)plan.tiles.size(); stats[1] = plan.max_cnt; stats[2] = plan.torsion_sines ? 1 : 0;
+        stats[3] = 0;
+        for (char c : plan.t_live) stats[3] += c ? 1 : 0;
+    }
+    return MLP_OK;
+}
 
 int mlp_device_count(void) {
     int n = 0;

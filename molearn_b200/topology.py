@@ -79,6 +79,21 @@ class Topology:
         n = self.n_atoms
         return n * (n - 1) // 2 - len(self.exclusions)
 
+    def bonded_plan(self, tile_atoms: int = 128):
+        """Work items of the bonded kernel for tiles of ``tile_atoms`` atoms (host-only; ``mlp_bonded_plan``).
+
+        Returns ``(items [n, 9] int32, stats)``; columns: tile, i, j, k, l, torsion id | -1, angle id | -1,
+        bond id | -1, bond-on-(j,k) flag.  An item is up to one torsion + one angle (i,j,k) + one bond
+        ((i,j) or (j,k)) on the same four atoms."""
+        L = _lib.lib()
+        n = ctypes.c_int64(0)
+        st = np.zeros(4, np.int64)
+        _lib.check(L.mlp_bonded_plan(self._h, tile_atoms, ctypes.byref(n), None, 0, _vp(st)))
+        items = np.zeros((n.value, 9), np.int32)
+        _lib.check(L.mlp_bonded_plan(self._h, tile_atoms, ctypes.byref(n), _vp(items), n.value, _vp(st)))
+        return items, dict(tiles=int(st[0]), max_contributions_per_atom=int(st[1]), torsion_sines=bool(st[2]),
+                           live_torsions=int(st[3]))
+
     def as_dict(self):
         """Arrays under the names the golden fixtures / oracle use."""
         return dict(bond_idxs=self.bond_idxs, angle_idxs=self.angle_idxs, torsion_idxs=self.torsion_idxs,

@@ -119,3 +119,53 @@ def test_builder_matches_python_oracle_on_random_peptides(param_dir):
         assert np.array_equal(t.amber_types, o["amber_types"]) and np.array_equal(t.atom_charges, o["atom_charges"])
         assert np.array_equal(t.atom_R, o["atom_R"]) and np.array_equal(t.atom_e, o["atom_e"])
         assert np.array_equal(t.exclusions, to.exclusion_pairs(o).reshape(-1, 2))
+
+
+@pytest.mark.parametrize("tile", [128, 96, 40])
+def test_bonded_work_plan_covers_every_term_once(case, golden_topo, param_dir, tile):
+    """Host logic of the bonded kernel (mlp_bonded_plan): every tile evaluates exactly the terms that touch
+    one of its atoms, each once, and an item's angle / bond sit on the item's own atoms in the positions the
+    kernel assumes (angle = (i,j,k) centred on j, bond = (i,j) or (j,k))."""
+    from molearn_b200 import Topology
+    g = golden_topo(case)
+    t = Topology(atominfo_from(g), param_dir=param_dir)
+    try:
+        items, st = t.bonded_plan(tile)
+    except ValueError as exc:          # more than 2 items per thread: mlp_energy_create retries with a smaller tile
+        assert "too dense" in str(exc) and case == "pep28" and tile > 64
+        return
+    n = t.n_atoms
+    assert st["tiles"] == -(-n // tile)
+    amp = t.torsion_para[:, 1, :] / t.torsion_para[:, 0, :]
+    live = np.flatnonzero(np.any(amp.astype(np.float32) != 0, axis=1))
+    assert st["live_torsions"] == len(live)
+    per_atom = np.zeros((st["tiles"], n), np.int64)
+    for T in range(st["tiles"]):
+        lo, hi = T * tile, min(n, (T + 1) * tile)
+        own = lambda idx: np.any((idx >= lo) & (idx < hi), axis=-1)
+        rows = items[items[:, 0] == T]
+        for col, table, want in ((5, t.torsion_idxs, live[own(t.torsion_idxs[live])]),
+                                 (6, t.angle_idxs, np.flatnonzero(own(t.angle_idxs))),
+                                 (7, t.bond_idxs, np.flatnonzero(own(t.bond_idxs)))):
+            got = rows[rows[:, col] >= 0, col]
+            assert len(got) == len(set(got.tolist())), (case, T, col)             # each term once per tile
+            assert set(got.tolist()) == set(want.tolist()), (case, T, col)       # and exactly the tile's terms
+        for r in rows:
+            a = r[1:5]
+            if r[5] >= 0:
+                q = t.torsion_idxs[r[5]]
+                assert list(a) == list(q) or list(a) == list(q[::-1])
+            if r[6] >= 0:
+                q = t.angle_idxs[r[6]]
+                assert a[1] == q[1] and {a[0], a[2]} == {q[0], q[2]}
+            if r[7] >= 0:
+                pair = (a[1], a[2]) if r[8] else (a[0], a[1])
+                assert set(pair) == set(t.bond_idxs[r[7]].tolist())
+            roles = 4 if r[5] >= 0 else 3 if r[6] >= 0 else 2
+            assert roles > 2 or r[7] >= 0                                        # no empty items
+            for x in a[:roles]:
+                per_atom[T, x] += 1
+        # gradient slots: contributions of a tile's own atoms fit the slot table
+        assert per_atom[T, lo:hi].max() <= st["max_contributions_per_atom"]
+    # the matching should leave few angles / bonds without a carrier: items <= torsions + angles (never the plain sum)
+    assert len(items) < len(live) + len(t.angle_idxs) + len(t.bond_idxs)
