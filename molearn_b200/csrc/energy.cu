@@ -892,7 +892,10 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
 
 // grad[b, n] (+)= w_nb[b] * (sum of the partial forces of every tile pair in n's tile row / column),
 // summed in list order: reproducible.
-constexpr int RED_PARTS = 4;     // warps of a reduction CTA: each sums one contiguous quarter of an atom's block list
+#ifndef RED_PARTS_N
+#define RED_PARTS_N 2
+#endif
+constexpr int RED_PARTS = RED_PARTS_N;     // warps of a reduction CTA: each sums one contiguous quarter of an atom's block list
 __global__ void __launch_bounds__(32 * RED_PARTS)
 nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_off, const int* __restrict__ red_list,
                  int n_pairs, int N, float* __restrict__ grad, long sgb, long sgc, long sgn,
