@@ -62,6 +62,9 @@ constexpr int NB_NI = 4;         // i-atoms per lane
 #define NB_WARPS_PER_CTA 1
 #endif
 constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each (1: a finished item frees its slot at once)
+#ifndef BONDED_CPC_MAX
+#define BONDED_CPC_MAX 32   // conformations per bonded CTA (the item records are read once per CTA)
+#endif
 #ifndef BONDED_MINB
 #define BONDED_MINB 5   // bonded CTAs per SM the register budget is sized for (5 x 128 threads x 96 registers)
 #endif
@@ -1723,7 +1726,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
             return MLP_E_ARG;
         }
         prof_begin(1);
-        int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
+        int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(BONDED_CPC_MAX, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
         dim3 grid(e->n_tiles, (unsigned)((B + cpc - 1) / cpc));
 #define BONDED_LAUNCH(G, S) bonded_kernel<G, S><<<grid, BT, e->bonded_smem, bstream>>>(e->d_tiles, e->d_halo, e->d_items, e->d_sg, e->d_cnt, \
             x, sxb, (int)sxc, (int)sxn, grad, sgb, (int)sgc, (int)sgn, weights, energies ? e_bonded : nullptr, (int)B, cpc, \
