@@ -41,7 +41,11 @@ static dual d_scale(dual a, double s) { dual r; r.v = a.v * s; for (int i = 0; i
 static dual d_sqrt(dual a) { dual r; r.v = sqrt(a.v); for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] / (2.0 * r.v); return r; }
 static dual d_cos(dual a) { dual r; r.v = cos(a.v); double s = -sin(a.v); for (int i = 0; i < ND; ++i) r.d[i] = s * a.d[i]; return r; }
 static dual d_atan2(dual y, dual x) {
-    dual r; r.v = atan2(y.v, x.v);
+    /* atan2(+-0, +-0): with exactly coincident atoms both arguments are signed zeros whose signs depend on the
+     * summation order of the dot products (torch's reductions and this loop can disagree: 0 vs +-pi, seen on a
+     * collapsed 51k-atom decode).  The convention pinned here - and implemented by the kernels - is phi = 0, the
+     * value torch returns for atan2(0, 0). */
+    dual r; r.v = (y.v == 0.0 && x.v == 0.0) ? 0.0 : atan2(y.v, x.v);
     double q = x.v * x.v + y.v * y.v;
     for (int i = 0; i < ND; ++i) r.d[i] = (x.v * y.d[i] - y.v * x.d[i]) / q;
     return r;

@@ -38,3 +38,21 @@ print("decoded energies", e.cpu().numpy())
 bad = (~torch.isfinite(e).all(dim=1)).nonzero().flatten().tolist()
 pick = bad[0] if bad else 0
 check(dec[pick:pick + 1].contiguous().cpu().numpy(), f"decoded point {pick} ({'non-finite' if bad else 'finite'})")
+
+
+def torsion_energy_torch(xyz, dtype):
+    """The reference's torsion formula (torch_protein_energy.py:295-304) on explicit lists, in the given dtype:
+    how far plain fp32 arithmetic sits from fp64 on this structure (conditioning of collapsed geometries)."""
+    xt = torch.from_numpy(xyz).to(dev, dtype)
+    idx = torch.from_numpy(topo["torsion_idxs"]).to(dev).long()
+    para = torch.from_numpy(topo["torsion_para"]).to(dev).float().to(dtype)      # fp32-rounded parameters, like the reference
+    b1 = xt[idx[:, 0]] - xt[idx[:, 1]]; b2 = xt[idx[:, 1]] - xt[idx[:, 2]]; b3 = xt[idx[:, 3]] - xt[idx[:, 2]]
+    c32 = torch.linalg.cross(b3, b2); c12 = torch.linalg.cross(b1, b2)
+    phi = torch.atan2((b2 * torch.linalg.cross(c32, c12)).sum(-1), b2.norm(dim=-1) * (c12 * c32).sum(-1))
+    e = (para[:, 1] / para[:, 0]) * (1 + torch.cos(para[:, 3] * phi[:, None] - para[:, 2]))
+    return float(e.sum().double())
+
+
+xd = dec[pick].contiguous().cpu().numpy()
+e64, e32 = torsion_energy_torch(xd, torch.float64), torsion_energy_torch(xd, torch.float32)
+print("torsion energy of that structure with the reference formula: fp64", e64, "fp32", e32, "rel", abs(e32 - e64) / abs(e64))
