@@ -408,6 +408,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     from molearn_b200 import TorchProteinEnergy, _lib
@@ -607,8 +608,8 @@ def main():
         ach = flops / (nb_ms * 1e-3) / 1e12
         out["roofline"] = {"kernel": "nb_kernel2<grad> (packed FP32 pair kernel)", "bound": "fp32", "achieved": ach, "peak": fp32_peak,
                            "unit": "TFLOP/s", "frac": ach / fp32_peak,
-                           "traffic": 1788928, "traffic_source": "dram__bytes_read+write of one launch, profiles/r01_summary.txt (inputs are L2-resident)",
-                           "measured_ffma_peak_tflops": 71.2, "fma_pipe_busy_pct_ncu": 72.2,
+                           "traffic": 1787904, "traffic_source": "dram__bytes_read+write of one launch, profiles/r01_summary.txt (inputs are L2-resident)",
+                           "measured_ffma_peak_tflops": 71.2, "fma_pipe_busy_pct_ncu": 72.7,
                            "peak_source": "148 SM x 128 FMA lanes x 2 x sm_max_mhz (FP32 pipe; no tensor cores on this path)",
                            "algorithmic_flops_per_launch": flops, "kernel_ms": nb_ms,
                            "share_of_step": nb_ms / (ms / args.steps),
@@ -633,7 +634,7 @@ def main():
             gbs = byts / (t_ms * 1e-3) / 1e9
             out["roofline_bonded"] = {"kernel": "bonded_kernel<grad>", "bound": "hbm", "batch": BB, "achieved": gbs,
                                       "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                                      "traffic": 168585984, "traffic_source": "dram__bytes_read+write of one launch at B=4096, profiles/r01_bonded_b4096.txt",
+                                      "traffic": 169336832, "traffic_source": "dram__bytes_read+write of one launch at B=4096, profiles/r01_bonded_b4096.txt",
                                       "algorithmic_bytes_per_launch": byts, "kernel_ms": t_ms,
                                       "conformations_per_s": BB / (t_ms * 1e-3)}
             del xb, gb, eb
