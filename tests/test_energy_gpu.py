@@ -354,3 +354,44 @@ def test_random_peptides_vs_oracle(dev, param_dir):
             for k, term in enumerate(TERMS):
                 assert abs(e[q, k] - we[k]) < TOL * abs(we[k]), (trial, sel_name, n, term, e[q, k], we[k])
                 assert rel(g[k, q], wg[k]) < TOL, (trial, sel_name, n, term, rel(g[k, q], wg[k]))
+
+
+def test_two_streams_one_handle_bit_identical(dev, energy_objs, golden_energy):
+    """Independent batches alternating over two CUDA streams through ONE handle (bench.py's two-stream leg): the
+    handle's private side stream and events must keep every batch's kernels ordered - results bit-identical to the
+    one-stream evaluation."""
+    tpe = energy_objs("bbcb")
+    x0 = torch.from_numpy(golden_energy("bbcb")["x"]).to(dev)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    xs = [(x0.repeat(8, 1, 1) + 0.05 * torch.randn((8 * x0.shape[0],) + tuple(x0.shape[1:]), generator=gen).to(dev)).permute(0, 2, 1)
+          for _ in range(6)]
+    want = [tpe.energy_and_gradient(x) for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    for rep in range(3):
+        got = []
+        for i, x in enumerate(xs):
+            with torch.cuda.stream(streams[i % 2]):
+                got.append(tpe.energy_and_gradient(x))
+        torch.cuda.synchronize()
+        for (e0, g0), (e1, g1) in zip(want, got):
+            assert torch.equal(e0, e1) and torch.equal(g0, g1)
+
+
+def test_conformation_extent_limit_is_reported(dev, energy_objs, golden_energy):
+    """The bonded kernel addresses one conformation with 32-bit element offsets; a layout that spans 2^31 elements
+    or more is refused with an error (never evaluated wrongly)."""
+    import ctypes
+    from molearn_b200 import _lib
+    tpe = energy_objs("bbcb")
+    dv = tpe._dev()
+    x = torch.from_numpy(golden_energy("bbcb")["x"][:1]).to(dev).permute(0, 2, 1).contiguous()
+    e = torch.empty((1, 4), device=dev)
+    L = _lib.lib()
+    nbytes = L.mlp_energy_workspace_bytes(dv._h, 1, _lib.TERM_BONDED, 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = L.mlp_energy_eval(dv._h, x.data_ptr(), 1, 0, 1, 2 ** 31 // (tpe.n_atoms - 1) + 1, e.data_ptr(), None, 0, 0, 0, None,
+                           _lib.TERM_BONDED, 0, ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+    assert rc == _lib.E_ARG and b"32-bit" in L.mlp_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
