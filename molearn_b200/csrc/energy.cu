@@ -902,7 +902,34 @@ constexpr int RED_PARTS = RED_PARTS_N;     // warps of a reduction CTA: each sum
 __global__ void __launch_bounds__(32 * RED_PARTS)
 nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_off, const int* __restrict__ red_list,
                  int n_pairs, int N, float* __restrict__ grad, long sgb, long sgc, long sgn,
-                 const float* __restrict__ weights, int accumulate, int skip_zero_weight) {
+                 const float* __restrict__ weights, int accumulate, int skip_zero_weight,
+                 const float* __restrict__ e_bonded, int n_tiles, const double* __restrict__ e_nb,
+                 float* __restrict__ energies /* null: no energy output */, uint32_t term_mask) {
+    if (energies && blockIdx.x == gridDim.x - 1) {
+        // the conformation's energies: fp64 sums of the kernels' partials in a fixed order (this used to be a fifth
+        // launch next to the reduction; the last CTA of each conformation's row does it now)
+        __shared__ double s_en[RED_PARTS];
+        const int b = blockIdx.y, tid = threadIdx.x;
+        double s = 0.0;
+        if (term_mask & MLP_TERM_NB)
+            for (int p = tid; p < n_pairs; p += 32 * RED_PARTS) s += e_nb[(long)b * n_pairs + p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((tid & 31) == 0) s_en[tid >> 5] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double v = s_en[0];
+#pragma unroll
+            for (int q = 1; q < RED_PARTS; ++q) v += s_en[q];
+            energies[4 * b + 3] = (float)v;
+        }
+        if (tid < 3) {
+            double v = 0.0;
+            if (term_mask & (1u << tid))
+                for (int t = 0; t < n_tiles; ++t) v += (double)e_bonded[((long)b * n_tiles + t) * 3 + tid];
+            energies[4 * b + tid] = (float)v;
+        }
+    }
     // CTA = 32 consecutive atoms of one conformation; warp `part` sums its share of the tile's partial blocks,
     // then part 0 adds the RED_PARTS sums in order: a fixed summation tree, reproducible, with 4x the loads in
     // flight of a one-thread-per-atom loop (the kernel is latency-bound: 30 MB out of L2 for the headline batch)
@@ -1711,7 +1738,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     // already queued on `stream`, join before the first kernel that touches the gradient again): it is
     // latency-bound at small batches and fills the pair kernel's tail.  Per-kernel timing keeps one stream.
     const bool fork = bonded && nonbonded && e->overlap && !e->profile;
-    bool finalize_on_side = false;
+    bool energies_done = false;
     cudaStream_t bstream = stream;
     if (fork) {
         CK(cudaEventRecord(e->ev_fork, stream));
@@ -1761,27 +1788,18 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
 #undef NB_LAUNCH
         prof_end(2);
         ++launches;
-        if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient
-        if (fork && energies && grad) {
-            // the energy sums only need the two kernels' partials: run them next to the force reduction
-            CK(cudaEventRecord(e->ev_fork, stream));
-            CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
-            finalize_kernel<<<(unsigned)B, 128, 0, e->side>>>(e_bonded, e->n_tiles, e_nb, e->n_pairs, energies, term_mask);
-            CK(cudaEventRecord(e->ev_join, e->side));
-            finalize_on_side = true;
-            ++launches;
-        }
+        if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient (and sums its energy partials)
         if (grad) {
             prof_begin(3);
             nb_reduce_kernel<<<dim3(e->n_nbt * (NB_T / 32), (unsigned)B), 32 * RED_PARTS, 0, stream>>>(fpart, e->d_red_off, e->d_red_list, e->n_pairs, N,
-                grad, sgb, sgc, sgn, weights, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0);
+                grad, sgb, sgc, sgn, weights, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0,
+                e_bonded, e->n_tiles, e_nb, energies, term_mask);
             prof_end(3);
             ++launches;
+            energies_done = energies != nullptr;
         }
     }
-    if (finalize_on_side) {
-        CK(cudaStreamWaitEvent(stream, e->ev_join, 0));
-    } else if (energies) {
+    if (energies && !energies_done) {
         finalize_kernel<<<(unsigned)B, 128, 0, stream>>>(e_bonded, e->n_tiles, e_nb, e->n_pairs, energies, term_mask);
         ++launches;
     }
