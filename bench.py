@@ -211,6 +211,22 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+    plain = None
+    if world == 1:
+        # the same scan decoding through network.decode as the reference writes it (Conv1d -> BatchNorm1d -> ReLU, NCHW)
+        ma.set_network(net, fuse_decoder=False)
+        ma.setup_grid(samples=warm, padding=0.1)
+        ma.scan_scores(targets=targets)
+        ma.setup_grid(samples=G, padding=0.1)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        ma.scan_scores(targets=targets)
+        p1.record()
+        torch.cuda.synchronize()
+        plain = {"value": G * G / (p0.elapsed_time(p1) * 1e-3), "unit": "points/s", "ms": p0.elapsed_time(p1),
+                 "mode": "network.decode unfused (separate BatchNorm, bias and ReLU kernels, NCHW)"}
+        ma.set_network(net)
     # share of the energy + RMSD kernels: the same batches without the decoder
     tpe = ma.physics()
     xb = torch.randn(256, frames.shape[1], 3, device=dev) * 5 + torch.from_numpy(frames[0]).to(dev)
@@ -254,7 +270,9 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
             "columns": int(rows.shape[1]), "gather_bytes": ma.scan_stats["gather_bytes"],
             "points_this_rank": ma.scan_stats["points_this_rank"],
             "energy_rmsd_kernels_ms_this_rank": score_ms, "energy_rmsd_share": score_ms / ms,
-            "decoder": "FoldingNet AutoEncoder(out_points=2145), random init seed 0, torch default conv math (cuDNN)",
+            "decoder": "FoldingNet AutoEncoder(out_points=2145), random init seed 0, evaluated by models.FusedDecoder (eval-mode BatchNorm "
+                       "folded, cuDNN conv+bias+relu, channels-last; torch default TF32 conv math)",
+            "plain_decode": plain,
             "wall_s": time.perf_counter() - t0}
 
 

@@ -50,7 +50,8 @@ RMSD_ALIGN = 1
 
 
 def library_path() -> str:
-    return _build.LIB
+    """The in-tree library; ``MOLEARN_B200_LIB`` points at another build of the same ABI (A/B timing of kernel variants)."""
+    return os.environ.get("MOLEARN_B200_LIB") or _build.LIB
 
 
 def lib():

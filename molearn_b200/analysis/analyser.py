@@ -73,10 +73,24 @@ class MolearnAnalysis:
         return None, 0, 1
 
     # -- registry (analyser.py:172-270) -----------------------------------------------------------
-    def set_network(self, network):
+    def set_network(self, network, fuse_decoder=True):
+        """``fuse_decoder``: on a CUDA device the grid scans decode through ``models.FusedDecoder`` - the same
+        FoldingNet decoder with eval-mode BatchNorm folded into the convolutions, fused bias + ReLU and
+        channels-last activations (a snapshot of the weights: call ``set_network`` again after training further).
+        Networks without the FoldingNet layout, CPU networks and ``fuse_decoder=False`` use ``network.decode``."""
         self.network = network
         self.network.eval()
         self.device = next(network.parameters()).device
+        self._fused_decode = None
+        if fuse_decoder and self.device.type == "cuda":
+            from ..models.fused_decoder import fuse_decoder as _fuse
+            self._fused_decode = _fuse(network)
+
+    def _decode(self, z):
+        """[b, latent] -> [b, n_atoms, 3] on the device (standardised units)."""
+        fused = getattr(self, "_fused_decode", None)
+        dec = fused(z) if fused is not None else self.network.decode(z)
+        return dec[:, :self.n_atoms, :]
 
     def set_dataset(self, key, data, atomselect="protein"):
         """``data``: any object with ``dataset`` ([F,N,3] or [F,3,N] tensor), ``std``, ``mean``,
@@ -224,7 +238,7 @@ class MolearnAnalysis:
         with torch.no_grad():
             for slc in self._slices(hi - lo):
                 z = z_all[slc]
-                dec = self.network.decode(z)[:, :self.n_atoms, :]
+                dec = self._decode(z)
                 rows[slc] = score(z, dec)
         if world > 1:
             full = torch.empty((world * per, n_cols), dtype=torch.float32, device=self.device)
@@ -278,7 +292,7 @@ class MolearnAnalysis:
         if s_key not in self.surfaces:
             def score(z, dec):
                 z2 = self.network.encode(dec)
-                dec2 = self.network.decode(z2)[:, :self.n_atoms, :]
+                dec2 = self._decode(z2)
                 d = (dec - dec2) * self.stdval
                 rmsd = d.pow(2).sum(dim=2).mean(dim=1).sqrt()
                 drift = (z - z2).pow(2).mean(dim=1).sqrt()

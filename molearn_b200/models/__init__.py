@@ -1,3 +1,4 @@
 from .folding_autoencoder import AutoEncoder
+from .fused_decoder import FusedDecoder, fuse_decoder
 
-__all__ = ["AutoEncoder"]
+__all__ = ["AutoEncoder", "FusedDecoder", "fuse_decoder"]

@@ -41,7 +41,7 @@ def analysis(murd_data):
 def decoded_angstrom(ma):
     with torch.no_grad():
         z = ma._encoded["grid"].reshape(-1, 2).to(ma.device)
-        return (ma.network.decode(z)[:, :ma.n_atoms, :] * ma.stdval + ma.meanval).double().cpu().numpy()
+        return (ma._decode(z) * ma.stdval + ma.meanval).double().cpu().numpy()       # the scans' own decode path
 
 
 def test_scan_physics_vs_oracle(analysis):
@@ -159,3 +159,34 @@ def test_geometry_scans_vs_numpy(analysis, murd_data):
     assert inv["dataset_inversions"].shape == (16,) and (inv["dataset_inversions"] == 0).all()   # MD frames: no D-residues
     bl = ma.get_bondlengths("train")
     assert abs(bl["dataset_bondlen"]["N-CA"].mean() - 1.46) < 0.03
+
+
+def test_fused_decoder_matches_plain_decode_gpu():
+    """models.FusedDecoder (BatchNorm folded, cuDNN fused conv+bias+relu, channels-last) against network.decode:
+    fp32 convolution math -> 1e-4; cuDNN's default TF32 math -> both sit within TF32 noise of each other."""
+    from molearn_b200.models import AutoEncoder, FusedDecoder
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    net = AutoEncoder(out_points=2145).to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(0.3 * torch.randn(m.num_features, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.weight.data.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.bias.data.copy_(0.2 * torch.randn(m.num_features, generator=g))
+    fused = FusedDecoder(net.decoder)
+    z = torch.rand(16, 2, device=dev) * 2 - 1
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        for tf32, tol in ((False, 1e-4), (True, 2e-2)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                want = net.decode(z)
+                got = fused(z)
+            assert got.shape == want.shape
+            err = float((got - want).norm() / want.norm())
+            assert err < tol, (tf32, err)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert fused.fused_ok, "cuDNN fused conv+bias+relu was not available: the decoder ran the unfused fallback"
