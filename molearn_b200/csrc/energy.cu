@@ -43,6 +43,7 @@
 #include <functional>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------
@@ -475,6 +476,9 @@ __device__ __forceinline__ float nb_pair_fast(float r2c, float Rij, float e12, f
 // Exact pair term (any distance), minus what the fast path added for this pair at the clamped
 // distance.  Rare path (clashing structures): kept out of line to protect the hot loop's registers
 // and instruction cache.  Returns (ds, dSl, dSc).
+#ifndef NB_DENSE_MODE
+#define NB_DENSE_MODE 1   // 1: items whose first step is dominated by close pairs evaluate their other steps exactly, without the fast path
+#endif
 #ifndef NB_FIX_INLINE
 #define NB_FIX_INLINE 1   // 1: the exact pair correction is inlined into the micro-tile fix (1.2x in the clash regime, hot loop unchanged)
 #endif
@@ -589,6 +593,67 @@ __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const fl
             }
         }
     }
+}
+
+// All 16 pairs of a micro-tile evaluated exactly (any distance), branch-free, WITHOUT the fast path: the mode for
+// collapsed structures (an untrained decoder's output), where nearly every pair is closer than 1.9 A and "fast path +
+// correction" would do the work twice.  4 MUFU per pair (rsqrt, 2 x ex2, one shared rcp).  Returns true if some allowed
+// pair was closer than sqrt(NB_THR2) (the caller leaves the mode when most lanes report none).
+template <bool GRAD, bool FULL, bool WFORM>
+__device__ __forceinline__ bool nb_micro_exact(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
+                                               const float2 (&pj)[4], uint32_t m16,
+                                               float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
+    float4 yi[NB_NI], yj[4];
+#pragma unroll
+    for (int a = 0; a < NB_NI; ++a) {
+        yi[a] = xi[a];
+        asm volatile("" : "+f"(yi[a].x), "+f"(yi[a].y), "+f"(yi[a].z), "+f"(yi[a].w));
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        yj[b] = xj[b];
+        asm volatile("" : "+f"(yj[b].x), "+f"(yj[b].y), "+f"(yj[b].z), "+f"(yj[b].w));
+    }
+    float rmin = 3.0e38f;
+#pragma unroll
+    for (int a = 0; a < NB_NI; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float dx = yi[a].x - yj[b].x, dy = yi[a].y - yj[b].y, dz = yi[a].z - yj[b].z;
+            float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const bool on = (m16 >> (4 * a + b)) & 1u;
+            float Rij = WFORM ? fmaf(pi[a].y, pj[b].x, pi[a].x * pj[b].y) : pi[a].x + pj[b].x;
+            float e12 = WFORM ? 1.f : pi[a].y * pj[b].y;
+            float qq = yi[a].w * yj[b].w;
+            r2 = on ? r2 : NB_MASKED_R2;
+            if (WFORM) Rij = on ? Rij : 0.f; else e12 = on ? e12 : 0.f;
+            qq = on ? qq : 0.f;
+            rmin = fmin3(rmin, r2, r2);
+            const float dinv = r2 > 0.f ? rsqrt_nr(r2) : 0.f;   // coincident atoms: zero force; NaN stays NaN
+            const float d = r2 * dinv;
+            const float ex1 = __expf(d - LJ_K), ex2 = __expf(d - C_K);
+            const bool far1 = d > LJ_K, far2 = d > C_K;
+            const float w1 = far1 ? d : ex1 - 1.f + LJ_K, w2 = far2 ? d : ex2 - 1.f + C_K;
+            const float iw = rcp_fast(w1 * w2);                  // w1 >= 0.9 - e^-1.9, w2 >= 0.4 - ... > 0: no overflow for finite input
+            const float iw1 = iw * w2, iw2 = iw * w1;
+            const float t = Rij * iw1;
+            const float t2 = t * t;
+            const float t6 = t2 * t2 * t2;
+            const float u6 = e12 * t6;
+            const float ec = qq * iw2;
+            float ulj;
+            if (FULL) { ulj = u6 * (t6 - 1.f); Sl = fmaf(u6, t6 - 2.f, Sl); }
+            else { ulj = u6 * t6; Sl += ulj; }
+            Sc += ec;
+            if (GRAD) {
+                const float dw1 = far1 ? 1.f : ex1, dw2 = far2 ? 1.f : ex2;
+                const float sf = (ulj * iw1 * dw1 + ec * iw2 * dw2) * dinv;
+                Fi[a].x = fmaf(sf, dx, Fi[a].x); Fi[a].y = fmaf(sf, dy, Fi[a].y); Fi[a].z = fmaf(sf, dz, Fi[a].z);
+                Fj[b].x = fmaf(sf, dx, Fj[b].x); Fj[b].y = fmaf(sf, dy, Fj[b].y); Fj[b].z = fmaf(sf, dz, Fj[b].z);
+            }
+        }
+    }
+    return !(rmin >= NB_THR2);
 }
 
 // One warp = one (conformation, tile pair).  Lane L owns i-atoms i0+4L+a (a<4) for the whole
@@ -833,44 +898,40 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     // bit r: rotation step r of this tile pair has an excluded pair in some lane (a band tile has 3 such steps of 32,
     // a diagonal tile 4-5 of 17 for backbone systems); the other steps run the mask-free micro-tile
     const uint32_t sbits = masked ? stepbits[IJ.z] : 0u;
-#pragma unroll 1
-    for (int r = r_begin; r < n_steps; ++r) {
-        const int g = (lane + r) & 31;
-        float4 cj[6];
+    // scalar path on un-packed views of the lane's data: DENSE = false: exact correction of the micro-tile's close pairs
+    // (rare); DENSE = true: exact evaluation of all 16 pairs instead of the fast path.  Returns nb_micro_exact's flag.
+    auto scalar_tile = [&](const float4 (&cj)[6], uint32_t m16, auto dense_tag) -> bool {
+        constexpr bool DENSE = decltype(dense_tag)::value;
+        float4 ui[NB_NI], uj[4];
+        float2 upi[NB_NI], upj[4];
+        float3 dFi[NB_NI], dFj[4];
+        float dSl = 0.f, dSc = 0.f;
+        bool any_close = false;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) cj[c] = s_j[c][g];
-        const bool mstep = (sbits >> r) & 1u;
-        const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
-        const bool close = mstep ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
-                                  : nb_micro2<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
-        if (close) {
-            // rare: exact correction through the scalar path (un-packed views of the same data)
-            float4 ui[NB_NI], uj[4];
-            float2 upi[NB_NI], upj[4];
-            float3 dFi[NB_NI], dFj[4];
-            float dSl = 0.f, dSc = 0.f;
-#pragma unroll
-            for (int a = 0; a < NB_NI; ++a) {
-                ui[a] = make_float4(xi[a][0].x, xi[a][1].x, xi[a][2].x, xi[a][3].x);
-                upi[a] = make_float2(hRi[a].x, sei[a].x);
-                dFi[a] = make_float3(0.f, 0.f, 0.f);
-            }
-            const float* cf = reinterpret_cast<const float*>(cj);
-#pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-                uj[bb] = make_float4(cf[0 * 4 + bb], cf[1 * 4 + bb], cf[2 * 4 + bb], cf[3 * 4 + bb]);
-                upj[bb] = make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
-                dFj[bb] = make_float3(0.f, 0.f, 0.f);
-            }
-            nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
-#pragma unroll
-            for (int a = 0; a < NB_NI; ++a) { Fi[a][0].x += dFi[a].x; Fi[a][1].x += dFi[a].y; Fi[a][2].x += dFi[a].z; }
-            Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
-            Fj[0][0].y += dFj[1].x; Fj[0][1].y += dFj[1].y; Fj[0][2].y += dFj[1].z;
-            Fj[1][0].x += dFj[2].x; Fj[1][1].x += dFj[2].y; Fj[1][2].x += dFj[2].z;
-            Fj[1][0].y += dFj[3].x; Fj[1][1].y += dFj[3].y; Fj[1][2].y += dFj[3].z;
-            Sl.x += dSl; Sc.x += dSc;
+        for (int a = 0; a < NB_NI; ++a) {
+            ui[a] = make_float4(xi[a][0].x, xi[a][1].x, xi[a][2].x, xi[a][3].x);
+            upi[a] = make_float2(hRi[a].x, sei[a].x);
+            dFi[a] = make_float3(0.f, 0.f, 0.f);
         }
+        const float* cf = reinterpret_cast<const float*>(cj);
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+            uj[bb] = make_float4(cf[0 * 4 + bb], cf[1 * 4 + bb], cf[2 * 4 + bb], cf[3 * 4 + bb]);
+            upj[bb] = make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
+            dFj[bb] = make_float3(0.f, 0.f, 0.f);
+        }
+        if (DENSE) any_close = nb_micro_exact<GRAD, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+        else nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+#pragma unroll
+        for (int a = 0; a < NB_NI; ++a) { Fi[a][0].x += dFi[a].x; Fi[a][1].x += dFi[a].y; Fi[a][2].x += dFi[a].z; }
+        Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
+        Fj[0][0].y += dFj[1].x; Fj[0][1].y += dFj[1].y; Fj[0][2].y += dFj[1].z;
+        Fj[1][0].x += dFj[2].x; Fj[1][1].x += dFj[2].y; Fj[1][2].x += dFj[2].z;
+        Fj[1][0].y += dFj[3].x; Fj[1][1].y += dFj[3].y; Fj[1][2].y += dFj[3].z;
+        Sl.x += dSl; Sc.x += dSc;
+        return any_close;
+    };
+    auto rotate = [&]() {
         if (GRAD) {
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp)
@@ -880,6 +941,33 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
                     Fj[pp][c].y = __shfl_sync(0xffffffffu, Fj[pp][c].y, src_lane);
                 }
         }
+    };
+    int r = r_begin;
+#pragma unroll 1
+    for (; r < n_steps; ++r) {
+        const int g = (lane + r) & 31;
+        float4 cj[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) cj[c] = s_j[c][g];
+        const bool mstep = (sbits >> r) & 1u;
+        const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
+        const bool close = mstep ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
+                                  : nb_micro2<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+        if (close) scalar_tile(cj, m16, std::false_type{});
+        rotate();
+        // collapsed structures (an untrained decoder's output): when at least half of the lanes met a close pair in the
+        // item's first step, the remaining steps are evaluated exactly, without the fast path (second loop)
+        if (NB_DENSE_MODE && r == r_begin && __popc(__ballot_sync(0xffffffffu, close)) >= 16) { ++r; break; }
+    }
+#pragma unroll 1
+    for (; r < n_steps; ++r) {
+        const int g = (lane + r) & 31;
+        float4 cj[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) cj[c] = s_j[c][g];
+        const uint32_t m16 = ((sbits >> r) & 1u) ? sm16[g * 32 + lane] : 0xffffu;
+        scalar_tile(cj, m16, std::true_type{});
+        rotate();
     }
     if (GRAD) {
         float* out = fpart + item * (6 * NB_T);
