@@ -1,11 +1,12 @@
 """Key raw metrics + per-function / per-opcode instruction shares of one kernel in an .ncu-rep (needs ncu on PATH).
-usage: python tools/ncu_brief.py report.ncu-rep [source.cu]"""
+usage: python tools/ncu_brief.py report.ncu-rep [source.cu [kernel-name-regex]]"""
 import csv, io, re, subprocess, sys
 from collections import Counter
 
 rep = sys.argv[1]
 srcfile = sys.argv[2] if len(sys.argv) > 2 else "molearn_b200/csrc/energy.cu"
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ksel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep, *ksel, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 d = dict(zip(rows[0], rows[2]))
 want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__shared_mem_per_block", "sm__warps_active.avg.per_cycle_active",
@@ -19,7 +20,7 @@ for k in want:
 for k in rows[0]:
     if "issue_stalled" in k and "per_issue_active" in k and float(d[k] or 0) > 0.1:
         print(f"{k.replace('smsp__average_warps_issue_stalled_', 'stall ').replace('_per_issue_active.ratio', ''):75s} {float(d[k]):.2f}")
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, *ksel, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 src = open(srcfile).read().split("\n")
 def region(l):
