@@ -158,7 +158,7 @@ class MolearnAnalysis:
             out = None
             with torch.no_grad():
                 for slc in self._slices(enc.shape[0]):
-                    batch = self.network.decode(enc[slc].to(self.device))[:, :self.n_atoms, :].cpu()
+                    batch = self._decode(enc[slc].to(self.device)).cpu()
                     if out is None:
                         out = torch.empty(enc.shape[0], *batch.shape[1:], dtype=batch.dtype)
                     out[slc] = batch
