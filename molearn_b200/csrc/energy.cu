@@ -595,67 +595,6 @@ __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const fl
     }
 }
 
-// All 16 pairs of a micro-tile evaluated exactly (any distance), branch-free, WITHOUT the fast path: the mode for
-// collapsed structures (an untrained decoder's output), where nearly every pair is closer than 1.9 A and "fast path +
-// correction" would do the work twice.  4 MUFU per pair (rsqrt, 2 x ex2, one shared rcp).  Returns true if some allowed
-// pair was closer than sqrt(NB_THR2) (the caller leaves the mode when most lanes report none).
-template <bool GRAD, bool FULL, bool WFORM>
-__device__ __forceinline__ bool nb_micro_exact(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
-                                               const float2 (&pj)[4], uint32_t m16,
-                                               float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
-    float4 yi[NB_NI], yj[4];
-#pragma unroll
-    for (int a = 0; a < NB_NI; ++a) {
-        yi[a] = xi[a];
-        asm volatile("" : "+f"(yi[a].x), "+f"(yi[a].y), "+f"(yi[a].z), "+f"(yi[a].w));
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        yj[b] = xj[b];
-        asm volatile("" : "+f"(yj[b].x), "+f"(yj[b].y), "+f"(yj[b].z), "+f"(yj[b].w));
-    }
-    float rmin = 3.0e38f;
-#pragma unroll
-    for (int a = 0; a < NB_NI; ++a) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const float dx = yi[a].x - yj[b].x, dy = yi[a].y - yj[b].y, dz = yi[a].z - yj[b].z;
-            float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const bool on = (m16 >> (4 * a + b)) & 1u;
-            float Rij = WFORM ? fmaf(pi[a].y, pj[b].x, pi[a].x * pj[b].y) : pi[a].x + pj[b].x;
-            float e12 = WFORM ? 1.f : pi[a].y * pj[b].y;
-            float qq = yi[a].w * yj[b].w;
-            r2 = on ? r2 : NB_MASKED_R2;
-            if (WFORM) Rij = on ? Rij : 0.f; else e12 = on ? e12 : 0.f;
-            qq = on ? qq : 0.f;
-            rmin = fmin3(rmin, r2, r2);
-            const float dinv = r2 > 0.f ? rsqrt_nr(r2) : 0.f;   // coincident atoms: zero force; NaN stays NaN
-            const float d = r2 * dinv;
-            const float ex1 = __expf(d - LJ_K), ex2 = __expf(d - C_K);
-            const bool far1 = d > LJ_K, far2 = d > C_K;
-            const float w1 = far1 ? d : ex1 - 1.f + LJ_K, w2 = far2 ? d : ex2 - 1.f + C_K;
-            const float iw = rcp_fast(w1 * w2);                  // w1 >= 0.9 - e^-1.9, w2 >= 0.4 - ... > 0: no overflow for finite input
-            const float iw1 = iw * w2, iw2 = iw * w1;
-            const float t = Rij * iw1;
-            const float t2 = t * t;
-            const float t6 = t2 * t2 * t2;
-            const float u6 = e12 * t6;
-            const float ec = qq * iw2;
-            float ulj;
-            if (FULL) { ulj = u6 * (t6 - 1.f); Sl = fmaf(u6, t6 - 2.f, Sl); }
-            else { ulj = u6 * t6; Sl += ulj; }
-            Sc += ec;
-            if (GRAD) {
-                const float dw1 = far1 ? 1.f : ex1, dw2 = far2 ? 1.f : ex2;
-                const float sf = (ulj * iw1 * dw1 + ec * iw2 * dw2) * dinv;
-                Fi[a].x = fmaf(sf, dx, Fi[a].x); Fi[a].y = fmaf(sf, dy, Fi[a].y); Fi[a].z = fmaf(sf, dz, Fi[a].z);
-                Fj[b].x = fmaf(sf, dx, Fj[b].x); Fj[b].y = fmaf(sf, dy, Fj[b].y); Fj[b].z = fmaf(sf, dz, Fj[b].z);
-            }
-        }
-    }
-    return !(rmin >= NB_THR2);
-}
-
 // One warp = one (conformation, tile pair).  Lane L owns i-atoms i0+4L+a (a<4) for the whole
 // tile; the 32 groups of 4 j-atoms rotate through the lanes (lane L works on group (L+r)%32 at
 // step r) together with their force accumulators, so Newton's third law costs 12 shuffles per
@@ -842,6 +781,87 @@ __device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const fl
     return !(rmin >= NB_THR2);
 }
 
+// All 16 pairs of a micro-tile evaluated EXACTLY (any distance), branch-free and packed like nb_micro2, without the fast
+// path: the second loop of nb_kernel2 uses it for items dominated by close pairs (collapsed structures - an untrained
+// decoder's output - where "fast path + correction" would do the work twice).  Per pair: 38 FMA-pipe lane-operations and
+// 4 MUFU (rsqrt, 2 x ex2, one shared rcp).  w(d,k) = elu(d-k)+k (torch_protein_energy.py:238-239).
+__device__ __forceinline__ float ex2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <bool GRAD, bool MASKED, bool FULL>
+__device__ __forceinline__ bool nb_micro2_exact(const float2 (&xi)[NB_NI][4], const float2 (&hRi)[NB_NI], const float2 (&sei)[NB_NI],
+                                                 const float4 (&cj)[6], uint32_t m16,
+                                                 float2 (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
+    constexpr bool WF = NB_WFORM && !FULL;
+    constexpr float LOG2E = 1.4426950408889634f;
+    float rmin = 3.0e38f;
+    const float2 neg1 = dup(-1.f), one = dup(1.f);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const float2 xj = p ? f2(cj[0].z, cj[0].w) : f2(cj[0].x, cj[0].y);
+        const float2 yj = p ? f2(cj[1].z, cj[1].w) : f2(cj[1].x, cj[1].y);
+        const float2 zj = p ? f2(cj[2].z, cj[2].w) : f2(cj[2].x, cj[2].y);
+        const float2 qj = p ? f2(cj[3].z, cj[3].w) : f2(cj[3].x, cj[3].y);
+        const float2 hj = p ? f2(cj[4].z, cj[4].w) : f2(cj[4].x, cj[4].y);
+        const float2 sj = p ? f2(cj[5].z, cj[5].w) : f2(cj[5].x, cj[5].y);
+#pragma unroll
+        for (int a = 0; a < NB_NI; ++a) {
+            float2 dx = __ffma2_rn(xj, neg1, xi[a][0]), dy = __ffma2_rn(yj, neg1, xi[a][1]), dz = __ffma2_rn(zj, neg1, xi[a][2]);
+            float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            float2 e12 = WF ? __ffma2_rn(sei[a], hj, __fmul2_rn(hRi[a], sj)) : __fmul2_rn(sei[a], sj);
+            float2 qq = __fmul2_rn(xi[a][3], qj);
+            float2 Rij = WF ? e12 : __ffma2_rn(hRi[a], one, hj);
+            if (MASKED) {
+                const bool on0 = (m16 >> (4 * a + 2 * p)) & 1u, on1 = (m16 >> (4 * a + 2 * p + 1)) & 1u;
+                r2.x = on0 ? r2.x : NB_MASKED_R2; r2.y = on1 ? r2.y : NB_MASKED_R2;
+                if (WF) { Rij.x = on0 ? Rij.x : 0.f; Rij.y = on1 ? Rij.y : 0.f; }
+                else { e12.x = on0 ? e12.x : 0.f; e12.y = on1 ? e12.y : 0.f; }
+                qq.x = on0 ? qq.x : 0.f; qq.y = on1 ? qq.y : 0.f;
+            }
+            rmin = fmin3(rmin, r2.x, r2.y);
+            // d = r2 * rsqrt(r2), one Newton step; coincident atoms: 1/d := 0 (zero force, like cdist's backward); NaN stays NaN
+            const float2 y0 = f2(rsqrt_fast(r2.x), rsqrt_fast(r2.y));
+            const float2 hn = __fmul2_rn(__fmul2_rn(r2, dup(-0.5f)), y0);
+            float2 dinv = __fmul2_rn(y0, __ffma2_rn(hn, y0, dup(1.5f)));
+            dinv.x = r2.x > 0.f ? dinv.x : 0.f; dinv.y = r2.y > 0.f ? dinv.y : 0.f;
+            const float2 d = __fmul2_rn(r2, dinv);
+            const float2 a1 = __ffma2_rn(d, dup(LOG2E), dup(-LJ_K * LOG2E)), a2 = __ffma2_rn(d, dup(LOG2E), dup(-C_K * LOG2E));
+            const float2 ex1 = f2(ex2_fast(a1.x), ex2_fast(a1.y)), ex2 = f2(ex2_fast(a2.x), ex2_fast(a2.y));
+            const float2 n1 = __ffma2_rn(ex1, one, dup(LJ_K - 1.f)), n2 = __ffma2_rn(ex2, one, dup(C_K - 1.f));
+            const bool f1x = d.x > LJ_K, f1y = d.y > LJ_K, f2x = d.x > C_K, f2y = d.y > C_K;
+            const float2 w1 = f2(f1x ? d.x : n1.x, f1y ? d.y : n1.y), w2 = f2(f2x ? d.x : n2.x, f2y ? d.y : n2.y);
+            const float2 ww = __fmul2_rn(w1, w2);
+            const float2 iw = f2(rcp_fast(ww.x), rcp_fast(ww.y));
+            const float2 iw1 = __fmul2_rn(iw, w2), iw2 = __fmul2_rn(iw, w1);
+            const float2 t = __fmul2_rn(Rij, iw1);
+            const float2 t2 = __fmul2_rn(t, t);
+            const float2 t6 = __fmul2_rn(__fmul2_rn(t2, t2), t2);
+            const float2 u6 = WF ? t6 : __fmul2_rn(e12, t6);
+            const float2 ec = __fmul2_rn(qq, iw2);
+            float2 ulj;
+            if (FULL) {
+                ulj = __fmul2_rn(u6, __ffma2_rn(t6, one, neg1));
+                Sl = __ffma2_rn(u6, __ffma2_rn(t6, one, dup(-2.f)), Sl);
+            } else {
+                ulj = __fmul2_rn(u6, t6);
+                Sl = __ffma2_rn(u6, t6, Sl);
+            }
+            Sc = __ffma2_rn(qq, iw2, Sc);
+            if (GRAD) {
+                const float2 dw1 = f2(f1x ? 1.f : ex1.x, f1y ? 1.f : ex1.y), dw2 = f2(f2x ? 1.f : ex2.x, f2y ? 1.f : ex2.y);
+                const float2 gl = __fmul2_rn(__fmul2_rn(ulj, iw1), dw1), gc = __fmul2_rn(__fmul2_rn(ec, iw2), dw2);
+                const float2 sf = __fmul2_rn(__ffma2_rn(gl, one, gc), dinv);
+                Fi[a][0] = __ffma2_rn(sf, dx, Fi[a][0]); Fi[a][1] = __ffma2_rn(sf, dy, Fi[a][1]); Fi[a][2] = __ffma2_rn(sf, dz, Fi[a][2]);
+                Fj[p][0] = __ffma2_rn(sf, dx, Fj[p][0]); Fj[p][1] = __ffma2_rn(sf, dy, Fj[p][1]); Fj[p][2] = __ffma2_rn(sf, dz, Fj[p][2]);
+            }
+        }
+    }
+    return !(rmin >= NB_THR2);
+}
+
 template <bool GRAD, bool FULL>
 __global__ void __launch_bounds__(32, 4 * NB2_MINB)
 nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const float* __restrict__ q, int N,
@@ -898,15 +918,12 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     // bit r: rotation step r of this tile pair has an excluded pair in some lane (a band tile has 3 such steps of 32,
     // a diagonal tile 4-5 of 17 for backbone systems); the other steps run the mask-free micro-tile
     const uint32_t sbits = masked ? stepbits[IJ.z] : 0u;
-    // scalar path on un-packed views of the lane's data: DENSE = false: exact correction of the micro-tile's close pairs
-    // (rare); DENSE = true: exact evaluation of all 16 pairs instead of the fast path.  Returns nb_micro_exact's flag.
-    auto scalar_tile = [&](const float4 (&cj)[6], uint32_t m16, auto dense_tag) -> bool {
-        constexpr bool DENSE = decltype(dense_tag)::value;
+    // exact correction of a micro-tile's close pairs (rare) through the scalar path, on un-packed views of the lane's data
+    auto fix_tile = [&](const float4 (&cj)[6], uint32_t m16) {
         float4 ui[NB_NI], uj[4];
         float2 upi[NB_NI], upj[4];
         float3 dFi[NB_NI], dFj[4];
         float dSl = 0.f, dSc = 0.f;
-        bool any_close = false;
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) {
             ui[a] = make_float4(xi[a][0].x, xi[a][1].x, xi[a][2].x, xi[a][3].x);
@@ -920,8 +937,7 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
             upj[bb] = make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
             dFj[bb] = make_float3(0.f, 0.f, 0.f);
         }
-        if (DENSE) any_close = nb_micro_exact<GRAD, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
-        else nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+        nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) { Fi[a][0].x += dFi[a].x; Fi[a][1].x += dFi[a].y; Fi[a][2].x += dFi[a].z; }
         Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
@@ -929,7 +945,6 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         Fj[1][0].x += dFj[2].x; Fj[1][1].x += dFj[2].y; Fj[1][2].x += dFj[2].z;
         Fj[1][0].y += dFj[3].x; Fj[1][1].y += dFj[3].y; Fj[1][2].y += dFj[3].z;
         Sl.x += dSl; Sc.x += dSc;
-        return any_close;
     };
     auto rotate = [&]() {
         if (GRAD) {
@@ -953,7 +968,7 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
         const bool close = mstep ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
                                   : nb_micro2<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
-        if (close) scalar_tile(cj, m16, std::false_type{});
+        if (close) fix_tile(cj, m16);
         rotate();
         // collapsed structures (an untrained decoder's output): when at least half of the lanes met a close pair in the
         // item's first step, the remaining steps are evaluated exactly, without the fast path (second loop)
@@ -965,8 +980,10 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         float4 cj[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) cj[c] = s_j[c][g];
-        const uint32_t m16 = ((sbits >> r) & 1u) ? sm16[g * 32 + lane] : 0xffffu;
-        scalar_tile(cj, m16, std::true_type{});
+        const bool mstep = (sbits >> r) & 1u;
+        const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
+        if (mstep) nb_micro2_exact<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+        else nb_micro2_exact<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
         rotate();
     }
     if (GRAD) {
