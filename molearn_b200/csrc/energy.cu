@@ -20,15 +20,18 @@
 //
 // Non-bonded kernel
 //   Work item = (conformation, 128x128 atom tile pair J>=I), one one-warp CTA each, tile pairs ordered
-//   longest first.  A lane owns NI=4 i-atoms in registers for the whole tile; the 32 groups of 4 j-atoms
-//   rotate through the lanes together with their force accumulators (Newton's third law for 12 shuffles per
-//   16 pairs; diagonal tiles need only 17 of the 32 rotation steps).  Tile pairs that contain excluded
-//   (1-2/1-3/1-4) pairs or the diagonal carry a 128x128 bit mask applied in registers.  The hot loop is the
-//   fast path w(d,k) = d at a clamped distance, written in packed FP32 (FFMA2/FMUL2 over two j-atoms per
-//   instruction: the scalar version was issue-bound, the packed one is FMA-pipe-bound); the rare pairs closer
-//   than 1.9 A are corrected exactly, out of line.  Each item writes its partial forces to a scratch buffer;
-//   a second kernel sums, per atom, the partials of the tile pairs in its row and column in a fixed order and
-//   adds them to the gradient.  nb_kernel (scalar) is kept for comparison (MLP_NB_PACKED=0).
+//   longest first (the diagonal tiles last, cut into two step ranges).  A lane owns NI=4 i-atoms in registers for
+//   the whole tile; the 32 groups of 4 j-atoms rotate through the lanes together with their force accumulators
+//   (Newton's third law for 12 shuffles per 16 pairs; diagonal tiles need only 17 of the 32 rotation steps).  Tile
+//   pairs that contain excluded (1-2/1-3/1-4) pairs or the diagonal carry a 128x128 bit mask, applied in registers
+//   in the rotation steps that touch an excluded pair.  The hot loop is the fast path w(d,k) = d at a clamped
+//   distance, written in packed FP32 (FFMA2/FMUL2 over two j-atoms per instruction: the scalar version was
+//   issue-bound, the packed one is FMA-pipe-bound); the rare pairs closer than 1.9 A are corrected exactly.  Items
+//   whose first step is dominated by close pairs (collapsed structures) run their other steps in a second loop that
+//   evaluates every pair exactly (packed as well) and skips the fast path.  Each item writes its partial forces to a
+//   scratch buffer; a second kernel sums, per atom, the partials of the tile pairs in its row and column in a fixed
+//   order, adds them to the gradient and reduces the conformation's energy partials.  nb_kernel (scalar) is kept
+//   for comparison (MLP_NB_PACKED=0).
 #include "../../include/molearn_b200.h"
 #include "topology.hpp"
 
