@@ -395,3 +395,27 @@ def test_conformation_extent_limit_is_reported(dev, energy_objs, golden_energy):
     assert rc == _lib.E_ARG and b"32-bit" in L.mlp_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc)
+
+
+@pytest.mark.parametrize("knob", ["MLP_NB_PACKED=0", "MLP_NO_OVERLAP=1", "MLP_BONDED_TILE=64", "MLP_BONDED_TILE=40"])
+def test_alternative_code_paths_agree(knob, dev, golden_topo, golden_energy, monkeypatch):
+    """The library's run-time switches (read when a handle is created) select other code paths of the same maths: the
+    scalar pair kernel, no side-stream overlap, smaller bonded tiles (other work-item matchings and halos).  Each must
+    meet the same tolerance against the reference's fp64 vectors."""
+    from molearn_b200 import TorchProteinEnergy
+    name, value = knob.split("=")
+    monkeypatch.setenv(name, value)
+    tpe = TorchProteinEnergy(None, atominfo_from(golden_topo("bbcb")), device=dev)
+    if name == "MLP_BONDED_TILE":
+        assert tpe._dev().info()["bonded_tile_atoms"] == int(value)
+    en = golden_energy("bbcb")
+    gf = list(en["grad_frames"])
+    x = torch.from_numpy(en["x"][gf]).to(dev).permute(0, 2, 1)
+    e = tpe.energy_per_conformation(x).double().cpu().numpy()
+    for k, term in enumerate(TERMS):
+        err = np.abs(e[:, k] - en["e64"][gf][:, k]) / np.abs(en["e64"][gf][:, k])
+        assert err.max() < TOL, (knob, term, err)
+    g = per_term_grads(tpe, x)
+    for k, term in enumerate(TERMS):
+        for q in range(len(gf)):
+            assert rel(g[k, q], en["g64"][q, k]) < TOL, (knob, term, q)
