@@ -135,6 +135,8 @@ def fuse_decoder(network):
     if the network does not have that structure (the caller then keeps ``network.decode``)."""
     dec = getattr(network, "decoder", None)
     try:
-        return FusedDecoder(dec) if dec is not None else None
-    except (AttributeError, TypeError):
+        if dec is None or next(dec.parameters()).dtype != torch.float32:     # the fused path computes in fp32 / TF32 only
+            return None
+        return FusedDecoder(dec)
+    except (AttributeError, TypeError, StopIteration):
         return None

@@ -84,3 +84,4 @@ def test_fused_decoder_accepts_the_reference_network():
         want = theirs.decode(z)
         assert torch.allclose(fused(z), want, rtol=1e-4, atol=1e-5 * float(want.abs().max()))
     assert fuse_decoder(torch.nn.Linear(2, 2)) is None
+    assert fuse_decoder(ref.AutoEncoder(out_points=300).double().eval()) is None     # fp32 networks only
