@@ -1,4 +1,5 @@
 // Microbenchmark: issue / pipe throughput of FFMA vs packed FFMA2 (fma.rn.f32x2) on sm_100a.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/ffma2_bench tools/micro/ffma2_bench.cu ; run it on a B200 (gpurun)
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int MODE>
