@@ -145,7 +145,8 @@ int mlp_energy_info(const mlp_energy* e, int64_t info[8]);
  *
  *   x          dev, logical shape [B,3,N] fp32 addressed as x[b*sxb + c*sxc + n*sxn]
  *              (the reference layout [B,3,N] contiguous is sxb=3N,sxc=N,sxn=1; a decoder output
- *              [B,M,3] sliced to N atoms is sxb=3M,sxc=1,sxn=3)
+ *              [B,M,3] sliced to N atoms is sxb=3M,sxc=1,sxn=3).  sxc, sxn >= 0 and one conformation must
+ *              span fewer than 2^31 elements ((N-1)*sxn + 2*sxc < 2^31; same for the gradient), else MLP_E_ARG.
  *   energies   dev [B,4] fp32 (bond, angle, torsion, nb) per conformation, or NULL.  Terms not
  *              in term_mask are written as 0.   (E-1..E-3, NB-2 of SURVEY 8a;
  *              torch_protein_energy.py:276-305, 224-239)
@@ -159,7 +160,9 @@ int mlp_energy_info(const mlp_energy* e, int64_t info[8]);
  * Concurrency: work is ordered on `stream`; when both bonded and non-bonded terms are requested the bonded
  * kernel runs on a private stream of the handle that forks from and joins back into `stream` (so the call is
  * still stream-ordered for the caller and capturable into a CUDA graph).  One handle serves one host thread at
- * a time; use one handle per device and per concurrently calling thread.
+ * a time; use one handle per device and per concurrently calling thread.  Independent batches may alternate
+ * over two streams through the same handle (calls from one thread): the next batch's pair kernel then fills
+ * the last wave of the current one.
  */
 int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B,
                     int64_t sxb, int64_t sxc, int64_t sxn,
