@@ -121,51 +121,82 @@ def test_builder_matches_python_oracle_on_random_peptides(param_dir):
         assert np.array_equal(t.exclusions, to.exclusion_pairs(o).reshape(-1, 2))
 
 
-@pytest.mark.parametrize("tile", [128, 96, 40])
-def test_bonded_work_plan_covers_every_term_once(case, golden_topo, param_dir, tile):
-    """Host logic of the bonded kernel (mlp_bonded_plan): every tile evaluates exactly the terms that touch
-    one of its atoms, each once, and an item's angle / bond sit on the item's own atoms in the positions the
-    kernel assumes (angle = (i,j,k) centred on j, bond = (i,j) or (j,k))."""
-    from molearn_b200 import Topology
-    g = golden_topo(case)
-    t = Topology(atominfo_from(g), param_dir=param_dir)
+def _check_bonded_plan(t, tile, label):
+    """Every tile evaluates exactly the terms that touch one of its atoms, each once; an item's angle / bond sit on
+    the item's own atoms in the positions the kernel assumes (angle = (i,j,k) centred on j, bond = (i,j) or (j,k)).
+    Returns False if the topology is too dense for this tile size (mlp_energy_create then retries smaller)."""
     try:
         items, st = t.bonded_plan(tile)
-    except ValueError as exc:          # more than 2 items per thread: mlp_energy_create retries with a smaller tile
-        assert "too dense" in str(exc) and case == "pep28" and tile > 64
-        return
+    except ValueError as exc:          # more than 2 items per thread
+        assert "too dense" in str(exc), label
+        return False
     n = t.n_atoms
     assert st["tiles"] == -(-n // tile)
     amp = t.torsion_para[:, 1, :] / t.torsion_para[:, 0, :]
     live = np.flatnonzero(np.any(amp.astype(np.float32) != 0, axis=1))
     assert st["live_torsions"] == len(live)
-    per_atom = np.zeros((st["tiles"], n), np.int64)
     for T in range(st["tiles"]):
         lo, hi = T * tile, min(n, (T + 1) * tile)
         own = lambda idx: np.any((idx >= lo) & (idx < hi), axis=-1)
         rows = items[items[:, 0] == T]
-        for col, table, want in ((5, t.torsion_idxs, live[own(t.torsion_idxs[live])]),
-                                 (6, t.angle_idxs, np.flatnonzero(own(t.angle_idxs))),
-                                 (7, t.bond_idxs, np.flatnonzero(own(t.bond_idxs)))):
+        for col, want in ((5, live[own(t.torsion_idxs[live])] if len(live) else live),
+                          (6, np.flatnonzero(own(t.angle_idxs)) if len(t.angle_idxs) else np.zeros(0, int)),
+                          (7, np.flatnonzero(own(t.bond_idxs)) if len(t.bond_idxs) else np.zeros(0, int))):
             got = rows[rows[:, col] >= 0, col]
-            assert len(got) == len(set(got.tolist())), (case, T, col)             # each term once per tile
-            assert set(got.tolist()) == set(want.tolist()), (case, T, col)       # and exactly the tile's terms
+            assert len(got) == len(set(got.tolist())), (label, T, col)             # each term once per tile
+            assert set(got.tolist()) == set(want.tolist()), (label, T, col)       # and exactly the tile's terms
+        per_atom = np.zeros(n, np.int64)
         for r in rows:
             a = r[1:5]
             if r[5] >= 0:
                 q = t.torsion_idxs[r[5]]
-                assert list(a) == list(q) or list(a) == list(q[::-1])
+                assert list(a) == list(q) or list(a) == list(q[::-1]), label
             if r[6] >= 0:
                 q = t.angle_idxs[r[6]]
-                assert a[1] == q[1] and {a[0], a[2]} == {q[0], q[2]}
+                assert a[1] == q[1] and {a[0], a[2]} == {q[0], q[2]}, label
             if r[7] >= 0:
                 pair = (a[1], a[2]) if r[8] else (a[0], a[1])
-                assert set(pair) == set(t.bond_idxs[r[7]].tolist())
+                assert set(pair) == set(t.bond_idxs[r[7]].tolist()), label
             roles = 4 if r[5] >= 0 else 3 if r[6] >= 0 else 2
-            assert roles > 2 or r[7] >= 0                                        # no empty items
+            assert roles > 2 or r[7] >= 0, label                                  # no empty items
             for x in a[:roles]:
-                per_atom[T, x] += 1
+                per_atom[x] += 1
         # gradient slots: contributions of a tile's own atoms fit the slot table
-        assert per_atom[T, lo:hi].max() <= st["max_contributions_per_atom"]
-    # the matching should leave few angles / bonds without a carrier: items <= torsions + angles (never the plain sum)
-    assert len(items) < len(live) + len(t.angle_idxs) + len(t.bond_idxs)
+        assert per_atom[lo:hi].max(initial=0) <= st["max_contributions_per_atom"], label
+    n_terms = len(live) + len(t.angle_idxs) + len(t.bond_idxs)
+    assert len(items) <= n_terms                                                  # the matching never adds work
+    return True
+
+
+@pytest.mark.parametrize("tile", [128, 96, 40])
+def test_bonded_work_plan_covers_every_term_once(case, golden_topo, param_dir, tile):
+    """Host logic of the bonded kernel (mlp_bonded_plan) on the golden systems."""
+    from molearn_b200 import Topology
+    t = Topology(atominfo_from(golden_topo(case)), param_dir=param_dir)
+    ok = _check_bonded_plan(t, tile, (case, tile))
+    assert ok or (case == "pep28" and tile > 64)
+    if ok and case == "bbcb":
+        items, _ = t.bonded_plan(tile)
+        assert len(items) < 0.45 * (len(t.torsion_idxs) + len(t.angle_idxs) + len(t.bond_idxs))   # backbone: ~3 terms per item
+
+
+def test_bonded_work_plan_on_random_peptides(param_dir):
+    """The same invariants on seeded random sequences over all 28 residue templates (all-atom and heavy-atom), with
+    tile sizes that put the tile boundaries anywhere."""
+    from molearn_b200 import Topology
+    from oracle import topology_oracle as to
+    at, _, _, _ = to.parse_forcefield(param_dir)
+    residues = sorted(at)
+    rng = np.random.default_rng(19)
+    checked = 0
+    for trial in range(6):
+        heavy = trial % 2 == 0
+        seq = [residues[i] for i in rng.integers(0, len(residues), int(rng.integers(3, 40)))]
+        rid, atoms = 0, []
+        for r in seq:
+            rid += 1
+            atoms += [(a, r, rid) for a in at[r] if not (heavy and a.startswith("H"))]
+        t = Topology(np.array(atoms, dtype=object), param_dir=param_dir)
+        for tile in (int(rng.integers(8, 64)), 64, 128):
+            checked += bool(_check_bonded_plan(t, tile, (trial, heavy, tile)))
+    assert checked >= 8
