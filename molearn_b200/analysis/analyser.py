@@ -123,6 +123,16 @@ class MolearnAnalysis:
             "Datasets have different mean or standard deviation. Have you set correct mean and std to the PDBData?"
         assert self.n_atoms == ds.shape[1], "Datasets have different number of atoms"
 
+    @property
+    def datasets(self):
+        """``{key: dataset tensor}`` (analyser.py:1195-1197)."""
+        return {key: bundle.dataset for key, bundle in self._datasets.items()}
+
+    @property
+    def encoded(self):
+        """``{key: encoded tensor}`` (analyser.py:1199-1201)."""
+        return dict(self._encoded)
+
     def get_dataset(self, key, scale=False):
         b = self._datasets[key]
         return b.scale() if scale else b.dataset

@@ -57,6 +57,17 @@ def test_shard_range_covers_everything():
             assert got == list(range(total))
 
 
+def test_registry_views():
+    """`datasets` / `encoded` read-only views (analyser.py:1195-1201) that the reference's GUI and plot code read."""
+    ma = make()
+    assert list(ma.datasets) == ["train"] and ma.datasets["train"].shape == ma.get_dataset("train").shape
+    ma.get_encoded("train")
+    ma.setup_grid(samples=4)
+    assert set(ma.encoded) == {"train", "grid"}
+    ma.encoded.pop("grid")                                # a copy: the registry itself is untouched
+    assert "grid" in ma.encoded
+
+
 def test_setup_grid_matches_reference_formula():
     """analyser.py:568-594: linspace over padded bounds, meshgrid (row = y), reshape(-1,1,2)."""
     ma = make()
