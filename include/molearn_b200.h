@@ -189,8 +189,12 @@ int mlp_energy_profile_read(mlp_energy* e, double ms[4], int64_t counts[4]);
  *   out      dev [B,K] fp32
  *   flags    MLP_RMSD_ALIGN: RMSD after optimal rigid superposition (Kabsch / Horn quaternion
  *            eigenvalue, fp64) - what biobox Molecule.rmsd computes at analyser.py:297, 671
+ *            MLP_RMSD_PAIRED: K must equal B; structure b is scored against target b only and
+ *            out is [B] (get_error: every structure against its own reconstruction,
+ *            analyser.py:277-305, without the B x B matrix)
  */
 #define MLP_RMSD_ALIGN 1u
+#define MLP_RMSD_PAIRED 2u
 int mlp_rmsd_eval(const float* x, int64_t B, int64_t N,
                   int64_t sxb, int64_t sxc, int64_t sxn, float scale, float shift,
                   const float* targets, int64_t K, float* out, uint32_t flags, void* stream);

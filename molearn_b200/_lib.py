@@ -47,6 +47,7 @@ NB_REPULSIVE, NB_FULL = 0, 1
 TOPO_FIX_H = 1
 EVAL_ACCUMULATE_GRAD = 1
 RMSD_ALIGN = 1
+RMSD_PAIRED = 2
 
 
 def library_path() -> str:

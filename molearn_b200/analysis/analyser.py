@@ -76,15 +76,31 @@ class MolearnAnalysis:
     def set_network(self, network, fuse_decoder=True):
         """``fuse_decoder``: on a CUDA device the grid scans decode through ``models.FusedDecoder`` - the same
         FoldingNet decoder with eval-mode BatchNorm folded into the convolutions, fused bias + ReLU and
-        channels-last activations (a snapshot of the weights: call ``set_network`` again after training further).
+        channels-last activations (a snapshot of the weights, rebuilt automatically when they change).
         Networks without the FoldingNet layout, CPU networks and ``fuse_decoder=False`` use ``network.decode``."""
         self.network = network
         self.network.eval()
         self.device = next(network.parameters()).device
         self._fused_decode = None
-        if fuse_decoder and self.device.type == "cuda":
+        self._fuse_wanted = bool(fuse_decoder) and self.device.type == "cuda"
+        self._fused_versions = None
+        self._refresh_fused()
+
+    def _param_versions(self):
+        dec = getattr(self.network, "decoder", self.network)
+        return tuple(t._version for t in list(dec.parameters()) + list(dec.buffers()))
+
+    def _refresh_fused(self):
+        """(Re)build the fused-decoder snapshot when the network's parameters or BatchNorm statistics were written
+        since the last snapshot (training further, ``load_state_dict``): tensors count their in-place writes."""
+        if not self._fuse_wanted:
+            return
+        versions = self._param_versions()
+        if versions != self._fused_versions:
             from ..models.fused_decoder import fuse_decoder as _fuse
-            self._fused_decode = _fuse(network)
+            self.network.eval()
+            self._fused_decode = _fuse(self.network)
+            self._fused_versions = versions
 
     def _decode(self, z):
         """[b, latent] -> [b, n_atoms, 3] on the device (standardised units)."""
@@ -165,6 +181,7 @@ class MolearnAnalysis:
         """Host copy of the decoded structures (reference behaviour).  The scans below do not use it."""
         if key not in self._decoded or update:
             enc = self.get_encoded(key)
+            self._refresh_fused()
             out = None
             with torch.no_grad():
                 for slc in self._slices(enc.shape[0]):
@@ -189,8 +206,7 @@ class MolearnAnalysis:
                 xb = ds[slc].to(self.device)
                 dec = self.network.decode(self.network.encode(xb))[:, :self.n_atoms, :]
                 tgt = (xb * self.stdval + self.meanval).contiguous()
-                full = rmsd_to_targets(dec, tgt, self.stdval, self.meanval, align=align)    # [b, b]; the diagonal pairs i with i
-                out.append(full.diagonal().cpu())
+                out.append(rmsd_to_targets(dec, tgt, self.stdval, self.meanval, align=align, paired=True).cpu())
         return torch.cat(out).numpy()
 
     def num_trainable_params(self):
@@ -240,6 +256,7 @@ class MolearnAnalysis:
         if "grid" not in self._encoded:
             raise ValueError("Call MolearnAnalysis.setup_grid before scanning")
         dist, rank, world = self._dist()
+        self._refresh_fused()
         grid = self._encoded["grid"]
         total = grid.shape[0]
         lo, hi, per = shard_range(total, rank, world)

@@ -11,29 +11,43 @@ import torch
 from .. import _lib
 
 
-def rmsd_to_targets(x, targets, scale: float = 1.0, shift: float = 0.0, align: bool = False):
+def _check_structures(x, what="x"):
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: the scan reducers need CUDA tensors (there is no CPU fallback)")
+    if x.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32, got {x.dtype}")
+    if x.dim() != 3 or x.shape[2] != 3:
+        raise ValueError(f"{what}: expected [B, N, 3], got {tuple(x.shape)}")
+
+
+def rmsd_to_targets(x, targets, scale: float = 1.0, shift: float = 0.0, align: bool = False, paired: bool = False):
     """RMSD ``sqrt(mean_atoms sum_xyz (x*scale+shift - t)^2)`` of every structure to every target
     (the intended per-point formula, SURVEY S-3/S-4).  ``align=True``: after optimal rigid
     superposition (Kabsch), the quantity biobox ``Molecule.rmsd`` returns in the reference.
 
     :param x: ``[B, N, 3]`` float32 CUDA tensor (any strides - e.g. a slice of a decoder output).
-    :param targets: ``[K, N, 3]`` float32 CUDA tensor, in the units of ``x*scale+shift``.
-    :returns: ``[B, K]`` float32.
+    :param targets: ``[K, N, 3]`` float32 CUDA tensor on the same device, in the units of ``x*scale+shift``.
+    :param paired: ``K == B`` and structure ``b`` is scored against target ``b`` only.
+    :returns: ``[B, K]`` float32 (``[B]`` when ``paired``).
     """
-    if not x.is_cuda:
-        raise RuntimeError("rmsd_to_targets needs CUDA tensors (there is no CPU fallback)")
+    _check_structures(x)
     if targets.dim() == 2:
         targets = targets.unsqueeze(0)
+    if targets.device != x.device:
+        raise ValueError(f"targets live on {targets.device}, x on {x.device}")
     B, N, _ = x.shape
-    assert targets.shape[1:] == (N, 3), f"targets {tuple(targets.shape)} do not match x {tuple(x.shape)}"
+    if tuple(targets.shape[1:]) != (N, 3):
+        raise ValueError(f"targets {tuple(targets.shape)} do not match x {tuple(x.shape)}")
     targets = targets.contiguous().float()
     K = targets.shape[0]
-    out = torch.empty((B, K), dtype=torch.float32, device=x.device)
+    if paired and K != B:
+        raise ValueError(f"paired RMSD needs one target per structure, got {K} targets for {B} structures")
+    out = torch.empty((B,) if paired else (B, K), dtype=torch.float32, device=x.device)
+    flags = (_lib.RMSD_ALIGN if align else 0) | (_lib.RMSD_PAIRED if paired else 0)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().mlp_rmsd_eval(x.data_ptr(), B, N, x.stride(0), x.stride(2), x.stride(1),
                                             float(scale), float(shift), targets.data_ptr(), K, out.data_ptr(),
-                                            _lib.RMSD_ALIGN if align else 0,
-                                            torch.cuda.current_stream(x.device).cuda_stream))
+                                            flags, torch.cuda.current_stream(x.device).cuda_stream))
     return out
 
 
@@ -90,6 +104,9 @@ class GeometryStats:
 
     def __call__(self, x, scale: float = 1.0):
         """x [B, N, 3] CUDA float32 (any strides) -> [B, 2*G+1]: (mean, std) per bond type, then inversions."""
+        _check_structures(x)
+        if x.device != self.pairs.device:
+            raise ValueError(f"x lives on {x.device}, the geometry tables on {self.pairs.device}")
         G = len(self.types)
         out = torch.empty((x.shape[0], 2 * G + 1), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):

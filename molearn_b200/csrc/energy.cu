@@ -393,11 +393,16 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
     for (int b = b0; b < b1; ++b, xb += sxb, gb += sgb) {
         float wb = 1.f, wa = 1.f, wt = 1.f;
         if (weights) { wb = weights[4 * b]; wa = weights[4 * b + 1]; wt = weights[4 * b + 2]; }
-        if (GRAD && accumulate && !e_part && (!do_b || wb == 0.f) && (!do_a || wa == 0.f) && (!do_t || wt == 0.f)) {
-            // backward correction with nothing to add for this conformation (CTA-uniform)
+        if (GRAD && weights && !e_part && (!do_b || wb == 0.f) && (!do_a || wa == 0.f) && (!do_t || wt == 0.f)) {
+            // every requested term of this conformation has zero upstream weight (CTA-uniform): nothing to add, or an
+            // exact zero to store - the coordinates are not even read, so a non-finite conformation cannot leak NaN * 0
+            if (!accumulate && tid < t.n_own) { float* g = gb + gofs; g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
             if (b + 1 < b1) prefetch(xb + sxb);
             continue;
         }
+        // a term with zero upstream weight is dropped like a term the item does not carry (its degenerate-geometry
+        // NaN must not reach the gradient as NaN * 0); its energy is still counted
+        const uint32_t wdrop = weights ? ((wt == 0.f ? IT_T : 0u) | (wa == 0.f ? IT_A : 0u) | (wb == 0.f ? IT_B : 0u)) : 0u;
         // stage coordinates (the previous iteration's term phase is over: everybody passed its second barrier)
 #pragma unroll
         for (int q = 0; q < PF; ++q) if (sidx[q] >= 0) scf[sidx[q]] = pf[q];
@@ -407,7 +412,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
         float eb = 0.f, ea = 0.f, et = 0.f;
 #pragma unroll
         for (int r = 0; r < RI; ++r)
-            if (ai[r]) item_term<GRAD, SG>(sc, slots, ri[r], rs[r], ri[r].flags, wb, wa, wt, eb, ea, et);
+            if (ai[r]) item_term<GRAD, SG>(sc, slots, ri[r], rs[r], ri[r].flags & ~wdrop, wb, wa, wt, eb, ea, et);
         if (e_part) { s_e[0][tid] = eb; s_e[1][tid] = ea; s_e[2][tid] = et; }
         __syncthreads();
         if (e_part && warp < 3) {
@@ -1121,26 +1126,40 @@ finalize_kernel(const float* __restrict__ e_bonded, int n_tiles, const double* _
     }
 }
 
-// RMSD of x*scale+shift to K targets: out[b,k] = sqrt(sum_{n,c} d^2 / N)
+// RMSD of x*scale+shift to K targets: out[b,k] = sqrt(sum_{n,c} d^2 / N).  One block scores a structure against up
+// to RMSD_KC targets, so the structure is read once per RMSD_KC targets (the targets stay in L2).
+// paired: one target per structure, target index = b (get_error: structure b against its own reconstruction).
+constexpr int RMSD_KC = 8;
 __global__ void __launch_bounds__(256)
 rmsd_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, float scale, float shift,
-            const float* __restrict__ targets, int N, int K, float* __restrict__ out) {
-    const int b = blockIdx.x, k = blockIdx.y;
-    const float* t = targets + (long)k * N * 3;
-    float s = 0.f;
+            const float* __restrict__ targets, int N, int K, int paired, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int k0 = paired ? b : blockIdx.y * RMSD_KC;
+    const int nk = paired ? 1 : min(RMSD_KC, K - k0);
+    const float* t = targets + (long)k0 * N * 3;
+    const long tstride = (long)N * 3;
+    float s[RMSD_KC];
+#pragma unroll
+    for (int k = 0; k < RMSD_KC; ++k) s[k] = 0.f;
     for (int e = threadIdx.x; e < 3 * N; e += blockDim.x) {
         int n = e / 3, c = e - 3 * n;
-        float v = fmaf(x[(long)b * sxb + c * sxc + (long)n * sxn], scale, shift) - t[e];
-        s = fmaf(v, v, s);
+        const float v = fmaf(x[(long)b * sxb + c * sxc + (long)n * sxn], scale, shift);
+#pragma unroll
+        for (int k = 0; k < RMSD_KC; ++k)
+            if (k < nk) { const float d = v - t[k * tstride + e]; s[k] = fmaf(d, d, s[k]); }
     }
-    __shared__ float red[8];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __shared__ float red[RMSD_KC][8];
+#pragma unroll
+    for (int k = 0; k < RMSD_KC; ++k) {
+        s[k] = warp_sum(s[k]);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = s[k];
+    }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32 * RMSD_KC && (threadIdx.x >> 5) < nk) {
+        const int k = threadIdx.x >> 5, l = threadIdx.x & 31;
+        float v = l < (int)(blockDim.x >> 5) ? red[k][l] : 0.f;
         v = warp_sum(v);
-        if (threadIdx.x == 0) out[(long)b * K + k] = sqrtf(v / (float)N);
+        if (l == 0) out[paired ? (long)b : (long)b * K + k0 + k] = sqrtf(v / (float)N);
     }
 }
 
@@ -1175,9 +1194,10 @@ __device__ double max_eig_sym4(double a[4][4]) {
 // All sums in fp64: the result is a small difference of large numbers.
 __global__ void __launch_bounds__(256)
 rmsd_aligned_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, float scale, float shift,
-                    const float* __restrict__ targets, int N, int K, float* __restrict__ out) {
-    const int b = blockIdx.x, k = blockIdx.y;
+                    const float* __restrict__ targets, int N, int K, int paired, float* __restrict__ out) {
+    const int b = blockIdx.x, k = paired ? b : blockIdx.y;
     const float* t = targets + (long)k * N * 3;
+    float* const o = out + (paired ? (long)b : (long)b * K + k);
     double acc[17];  // sum x (3), sum t (3), sum |x|^2, sum |t|^2, sum x_i t_j (9)
 #pragma unroll
     for (int i = 0; i < 17; ++i) acc[i] = 0.0;
@@ -1219,8 +1239,7 @@ rmsd_aligned_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, f
             {S[0][1] - S[1][0], S[2][0] + S[0][2], S[1][2] + S[2][1], -S[0][0] - S[1][1] + S[2][2]}};
         double lam = max_eig_sym4(Km);
         double msd = (gx + gt - 2.0 * lam) / n;
-        out[(long)b * K + k] = (float)sqrt(fmax(msd, 0.0));
-        if (msd != msd) out[(long)b * K + k] = (float)msd;
+        *o = msd != msd ? (float)msd : (float)sqrt(fmax(msd, 0.0));
     }
 }
 
@@ -1823,10 +1842,26 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     const Workspace W = layout(e, B, term_mask, grad != nullptr);
     if (workspace_bytes < (int64_t)W.total) { mlp_set_error("mlp_energy_eval: workspace too small"); return MLP_E_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(workspace) & 15) { mlp_set_error("mlp_energy_eval: workspace must be 16-byte aligned"); return MLP_E_ARG; }
+    {   // every argument is checked before any device state (current device, events, side stream) is touched
+        auto fits = [&](int64_t sc, int64_t sn) { return sc >= 0 && sn >= 0 && (int64_t)(e->N - 1) * sn + 2 * sc < ((int64_t)1 << 31); };
+        if (!fits(sxc, sxn) || (grad && !fits(sgc, sgn))) {
+            mlp_set_error("mlp_energy_eval: one conformation is addressed with 32-bit element offsets "
+                          "(strides must be non-negative and a conformation must span less than 2^31 elements)");
+            return MLP_E_ARG;
+        }
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    int prev = 0;
-    CK(cudaGetDevice(&prev));
-    if (prev != e->device) CK(cudaSetDevice(e->device));
+    struct DeviceGuard {     // restores the caller's current device on every return path
+        int prev = -1, want;
+        explicit DeviceGuard(int w) : want(w) {}
+        cudaError_t enter() {
+            cudaError_t r = cudaGetDevice(&prev);
+            if (r == cudaSuccess && prev != want) r = cudaSetDevice(want);
+            return r;
+        }
+        ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+    } guard(e->device);
+    CK(guard.enter());
     char* ws = static_cast<char*>(workspace);
     ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
     float* e_bonded = reinterpret_cast<float*>(ws + W.e_bonded);
@@ -1858,12 +1893,6 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         bstream = e->side;
     }
     if (bonded) {
-        auto fits = [&](int64_t sc, int64_t sn) { return sc >= 0 && sn >= 0 && (int64_t)(N - 1) * sn + 2 * sc < ((int64_t)1 << 31); };
-        if (!fits(sxc, sxn) || (grad && !fits(sgc, sgn))) {
-            mlp_set_error("mlp_energy_eval: the bonded kernel addresses one conformation with 32-bit element offsets "
-                          "(strides must be non-negative and a conformation must span less than 2^31 elements)");
-            return MLP_E_ARG;
-        }
         prof_begin(1);
         int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(BONDED_CPC_MAX, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
         dim3 grid(e->n_tiles, (unsigned)((B + cpc - 1) / cpc));
@@ -1917,7 +1946,6 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     }
     e->last_launches = launches;
     cudaError_t err = cudaGetLastError();
-    if (prev != e->device) cudaSetDevice(prev);
     if (err != cudaSuccess) { mlp_set_error(std::string("kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
     return MLP_OK;
 }
@@ -1925,12 +1953,19 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
 int mlp_rmsd_eval(const float* x, int64_t B, int64_t N, int64_t sxb, int64_t sxc, int64_t sxn, float scale, float shift,
                   const float* targets, int64_t K, float* out, uint32_t flags, void* stream_) {
     if (B == 0) return MLP_OK;
-    if (!x || !targets || !out || B < 0 || N <= 0 || K <= 0 || K > 65535 || (flags & ~MLP_RMSD_ALIGN)) { mlp_set_error("mlp_rmsd_eval: bad argument"); return MLP_E_ARG; }
+    const bool paired = flags & MLP_RMSD_PAIRED;
+    if (!x || !targets || !out || B < 0 || N <= 0 || K <= 0 || (flags & ~(MLP_RMSD_ALIGN | MLP_RMSD_PAIRED)) ||
+        (paired && K != B) || (!paired && K > 65535 * (int64_t)RMSD_KC)) {
+        mlp_set_error("mlp_rmsd_eval: bad argument (paired mode needs K == B)");
+        return MLP_E_ARG;
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (flags & MLP_RMSD_ALIGN)
-        rmsd_aligned_kernel<<<dim3((unsigned)B, (unsigned)K), 256, 0, stream>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, out);
-    else
-        rmsd_kernel<<<dim3((unsigned)B, (unsigned)K), 256, 0, stream>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, out);
+    if (flags & MLP_RMSD_ALIGN) {
+        if (!paired && K > 65535) { mlp_set_error("mlp_rmsd_eval: at most 65535 targets with MLP_RMSD_ALIGN"); return MLP_E_ARG; }
+        rmsd_aligned_kernel<<<dim3((unsigned)B, paired ? 1u : (unsigned)K), 256, 0, stream>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, (int)paired, out);
+    } else {
+        rmsd_kernel<<<dim3((unsigned)B, paired ? 1u : (unsigned)((K + RMSD_KC - 1) / RMSD_KC)), 256, 0, stream>>>(x, sxb, sxc, sxn, scale, shift, targets, (int)N, (int)K, (int)paired, out);
+    }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { mlp_set_error(std::string("rmsd kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
     return MLP_OK;

@@ -34,32 +34,52 @@ class _DeviceEnergy:
         _lib.check(_lib.lib().mlp_energy_create(topology.handle, idx, nb_mode, ctypes.byref(self._h)))
         self.launches = 0  # kernels launched through this handle (bench.py reports it)
         self._ws_bytes = {}
+        self._ws = None
 
     # scratch memory per call is capped: larger batches are evaluated in chunks of conformations
-    MAX_BATCH_PER_CALL = 32768      # grid.y of the per-conformation kernels is limited to 65535
+    MAX_BATCH_PER_CALL = 32768      # the library takes at most 65535 conformations per call; chunks stay well below
     MAX_WORKSPACE_BYTES = int(float(__import__("os").environ.get("MLP_MAX_WORKSPACE_GB", "8")) * 2 ** 30)
+
+    def _workspace_bytes(self, B, term_mask, want_grad):
+        key = (B, term_mask, want_grad)
+        nbytes = self._ws_bytes.get(key)
+        if nbytes is None:
+            nbytes = self._ws_bytes[key] = _lib.lib().mlp_energy_workspace_bytes(self._h, B, term_mask, int(want_grad))
+        return nbytes
+
+    def _workspace(self, nbytes, device):
+        """Scratch buffer of the call.  The last one is kept and handed out again: allocations made on one stream
+        are reused by later calls on the same stream only (the caching allocator's rule, applied by hand)."""
+        stream = torch.cuda.current_stream(device)
+        ws = self._ws
+        if ws is None or ws[0].numel() < nbytes or ws[1] != stream.cuda_stream:
+            ws = self._ws = (torch.empty(nbytes, dtype=torch.uint8, device=device), stream.cuda_stream)
+        return ws[0], stream.cuda_stream
 
     def eval(self, x, energies, grad, weights, term_mask, accumulate=False):
         """x: [B,3,N] logical fp32 CUDA tensor (any strides). energies [B,4] or None; grad like x or None."""
+        B = x.shape[0]
+        want_grad = grad is not None
+        chunk = min(B, self.MAX_BATCH_PER_CALL)
+        # halve the chunk until its workspace fits (the library's sizes are not exactly linear in B: alignment slack)
+        while chunk > 1 and self._workspace_bytes(chunk, term_mask, want_grad) > self.MAX_WORKSPACE_BYTES:
+            chunk = (chunk + 1) // 2
+        if chunk >= B:
+            return self._eval_one(x, energies, grad, weights, term_mask, accumulate)
+        for lo in range(0, B, chunk):
+            sl = slice(lo, min(B, lo + chunk))
+            self._eval_one(x[sl], None if energies is None else energies[sl], None if grad is None else grad[sl],
+                           None if weights is None else weights[sl], term_mask, accumulate)
+
+    def _eval_one(self, x, energies, grad, weights, term_mask, accumulate):
         L = _lib.lib()
         B = x.shape[0]
-        key = (B, term_mask, grad is not None)
-        nbytes = self._ws_bytes.get(key)
-        if nbytes is None:
-            nbytes = self._ws_bytes[key] = L.mlp_energy_workspace_bytes(self._h, B, term_mask, int(grad is not None))
-        if (nbytes > self.MAX_WORKSPACE_BYTES or B > self.MAX_BATCH_PER_CALL) and B > 1:
-            per = max(1, (nbytes - 512) // B)
-            chunk = max(1, min(self.MAX_BATCH_PER_CALL, int(self.MAX_WORKSPACE_BYTES // per)))
-            for lo in range(0, B, chunk):
-                sl = slice(lo, min(B, lo + chunk))
-                self.eval(x[sl], None if energies is None else energies[sl], None if grad is None else grad[sl],
-                          None if weights is None else weights[sl], term_mask, accumulate)
-            return
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        gs = (grad.stride(0), grad.stride(1), grad.stride(2)) if grad is not None else (0, 0, 0)
-        stream = torch.cuda.current_stream(x.device).cuda_stream
+        nbytes = self._workspace_bytes(B, term_mask, grad is not None)
+        ws, stream = self._workspace(nbytes, x.device)
+        gs = grad.stride() if grad is not None else (0, 0, 0)
+        xs = x.stride()
         _lib.check(L.mlp_energy_eval(
-            self._h, x.data_ptr(), B, x.stride(0), x.stride(1), x.stride(2),
+            self._h, x.data_ptr(), B, xs[0], xs[1], xs[2],
             energies.data_ptr() if energies is not None else None,
             grad.data_ptr() if grad is not None else None, gs[0], gs[1], gs[2],
             weights.data_ptr() if weights is not None else None,
@@ -95,14 +115,17 @@ class _DeviceEnergy:
                 pass
 
 
-def _check_input(x, n_atoms):
+def _check_input(x, n_atoms, device=None):
     if not x.is_cuda:
         raise RuntimeError("molearn_b200 energy kernels need a CUDA tensor (there is no CPU fallback)")
     if x.dim() != 3 or x.shape[1] != 3:
         raise ValueError(f"expected coordinates of shape [B, 3, N], got {tuple(x.shape)}")
-    assert x.shape[2] == n_atoms, f"expected {n_atoms} atoms, got {x.shape[2]}"
+    if x.shape[2] != n_atoms:
+        raise ValueError(f"expected {n_atoms} atoms, got {x.shape[2]}")
     if x.dtype != torch.float32:
         raise TypeError("coordinates must be float32")
+    if device is not None and x.device.index != device:
+        raise ValueError(f"coordinates live on cuda:{x.device.index}, the energy object on cuda:{device}")
 
 
 class _EnergyFunction(torch.autograd.Function):
@@ -110,7 +133,7 @@ class _EnergyFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, dev: _DeviceEnergy, term_mask: int):
-        _check_input(x, dev.topology.n_atoms)
+        _check_input(x, dev.topology.n_atoms, dev.index)
         xd = x.detach()
         energies = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
         need_grad = ctx.needs_input_grad[0]
@@ -133,22 +156,18 @@ class _EnergyFunction(torch.autograd.Function):
         x, saved = ctx.saved_tensors
         if saved is None:
             raise RuntimeError("TorchProteinEnergy: backward through a forward that did not record a gradient")
-        terms = [t for t in range(4) if ctx.term_mask >> t & 1]
         if gout.stride() == (0, 0):
             # upstream is one scalar broadcast over [B,4] (e.g. ``E.sum().backward()``): every term of every
             # conformation has the same weight, so the saved unit-weight gradient only needs scaling
             return saved * gout.reshape(-1)[0].to(saved.dtype), None, None
-        gout = gout.contiguous().float()
-        t0 = terms[0]
-        # dL/dx = sum_t gout[b,t] dE_t/dx = gout[b,t0] * (saved = sum_t dE_t/dx) + sum_{t>t0} (gout[b,t]-gout[b,t0]) dE_t/dx
-        gin = saved * gout[:, t0].view(-1, 1, 1)
-        if len(terms) > 1:
-            w = gout - gout[:, t0:t0 + 1]
-            corr_mask = ctx.term_mask & ~(1 << t0)
-            with torch.cuda.device(x.device):
-                # conformations whose correction weights are all zero (the usual case: the loss
-                # sums the terms) exit early inside the kernels
-                ctx.dev.eval(x, None, gin, w.contiguous(), corr_mask, accumulate=True)
+        # General upstream gradient: dL/dx = sum_t gout[b,t] dE_t/dx is evaluated by the kernels with gout as per-term,
+        # per-conformation weights.  A term whose weight is zero is skipped inside the kernels, so a non-finite term or
+        # conformation that the loss masked out (torch.where / nansum, torch_physics_trainer.py:40-42) cannot reach
+        # the network as NaN * 0; scaling the saved sum of all terms would let it through.
+        gin = torch.empty_like(saved)
+        w = gout.contiguous().float()
+        with torch.cuda.device(x.device):
+            ctx.dev.eval(x, None, gin, w, ctx.term_mask)
         return gin, None, None
 
 
@@ -222,7 +241,7 @@ class TorchProteinEnergy:
         """Energies ``[B, 4]`` and the gradient of their sum ``dE/dx`` (same logical shape as ``x``) in one
         fused pass, without building an autograd graph - the call for scoring / sampling loops that consume
         forces directly.  Optional preallocated outputs are written in place."""
-        _check_input(x, self.n_atoms)
+        _check_input(x, self.n_atoms, self._dev().index)
         x = x.detach()
         if energies is None:
             energies = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)

@@ -120,6 +120,8 @@ class FusedDecoder:
             try:
                 first = fold1(self._assemble([g, x], fold1.in_channels), self.fused_ok)[:, :, :fold1.out_channels]
                 second = fold2(self._assemble([g, x, first], fold2.in_channels), self.fused_ok)[:, :, :fold2.out_channels]
+            except torch.cuda.OutOfMemoryError:
+                raise                                                # not a missing kernel: the caller must see it
             except RuntimeError:
                 if not self.fused_ok:
                     raise
