@@ -103,6 +103,11 @@ int mlp_topology_atoms(const mlp_topology* t, char* names, char* resnames, char*
 /* 1-4 pairs in torsion order [n_14,2] (bond_14_idxs, utils.py:687; computed, unused by E). */
 int mlp_topology_pairs14(const mlp_topology* t, int32_t* pairs14);
 
+/* The 1-4 scaled parameter arrays of utils.py:833-836, [n_14] fp32 each, in the reference's fp32 arithmetic:
+ * vdw_14R = 0.5*(R_i+R_j), vdw_14e = sqrt(e_i+e_j) (sic), q1q2_14 = q_i*q_j.  The reference computes them and
+ * never uses them in an energy; they are exported for callers that add a scaled 1-4 term.  Any pointer may be NULL. */
+int mlp_topology_params14(const mlp_topology* t, float* vdw_14R, float* vdw_14e, float* q1q2_14);
+
 void mlp_topology_destroy(mlp_topology* t);
 
 /* ---------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ SYMBOLS = {
     "mlp_topology_export": (c_int, [c_void_p] + [c_void_p] * 7),
     "mlp_topology_atoms": (c_int, [c_void_p] + [c_void_p] * 6),
     "mlp_topology_pairs14": (c_int, [c_void_p, c_void_p]),
+    "mlp_topology_params14": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "mlp_topology_destroy": (None, [c_void_p]),
     "mlp_bonded_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "mlp_device_count": (c_int, []),

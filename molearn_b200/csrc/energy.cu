@@ -728,10 +728,51 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
 
+// The lane's i-atom values enter every packed operation as (v, v).  NB_ISCALAR = 0 keeps them duplicated in
+// register pairs (one FFMA2 per use); NB_ISCALAR = 1 keeps one copy and spends two scalar FFMA/FMUL/FADD per use:
+// the same FMA-pipe cycles, twice the issue slots, 28 registers fewer (a fourth resident warp per scheduler).
+// NB_FISCALAR likewise folds the (even j, odd j) halves of the i-force accumulators on the fly (12 registers).
+#ifndef NB_ISCALAR
+#define NB_ISCALAR 0
+#endif
+#ifndef NB_FISCALAR
+#define NB_FISCALAR 0
+#endif
+#if NB_ISCALAR
+typedef float ival;
+__device__ __forceinline__ ival imake(float v) { return v; }
+__device__ __forceinline__ float ilo(ival v) { return v; }
+__device__ __forceinline__ float2 isub(float2 xj, ival xi) { return make_float2(xi - xj.x, xi - xj.y); }
+__device__ __forceinline__ float2 imul(ival a, float2 b) { return make_float2(a * b.x, a * b.y); }
+__device__ __forceinline__ float2 ifma(ival a, float2 b, float2 c) { return make_float2(fmaf(a, b.x, c.x), fmaf(a, b.y, c.y)); }
+__device__ __forceinline__ float2 iadd(ival a, float2 b) { return make_float2(a + b.x, a + b.y); }
+#else
+typedef float2 ival;
+__device__ __forceinline__ ival imake(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float ilo(ival v) { return v.x; }
+__device__ __forceinline__ float2 isub(float2 xj, ival xi) { return __ffma2_rn(xj, make_float2(-1.f, -1.f), xi); }
+__device__ __forceinline__ float2 imul(ival a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 ifma(ival a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 iadd(ival a, float2 b) { return __ffma2_rn(a, make_float2(1.f, 1.f), b); }   // add.f32x2 is lowered to two FADDs; FFMA2 by one stays packed
+#endif
+#if NB_FISCALAR
+typedef float fval;
+__device__ __forceinline__ fval fzero() { return 0.f; }
+__device__ __forceinline__ void facc(fval& F, float2 s, float2 d) { F = fmaf(s.x, d.x, fmaf(s.y, d.y, F)); }
+__device__ __forceinline__ float fsum(fval F) { return F; }
+__device__ __forceinline__ void faddlo(fval& F, float v) { F += v; }
+#else
+typedef float2 fval;
+__device__ __forceinline__ fval fzero() { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ void facc(fval& F, float2 s, float2 d) { F = __ffma2_rn(s, d, F); }
+__device__ __forceinline__ float fsum(fval F) { return F.x + F.y; }
+__device__ __forceinline__ void faddlo(fval& F, float v) { F.x += v; }
+#endif
+
 template <bool GRAD, bool MASKED, bool FULL>
-__device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const float2 (&hRi)[NB_NI], const float2 (&sei)[NB_NI],
+__device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival (&hRi)[NB_NI], const ival (&sei)[NB_NI],
                                            const float4 (&cj)[6], uint32_t m16,
-                                           float2 (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
+                                           fval (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
     constexpr bool WF = NB_WFORM && !FULL;
     float rmin = 3.0e38f;
     const float2 neg1 = dup(-1.f), one = dup(1.f);
@@ -745,12 +786,12 @@ __device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const fl
         const float2 sj = p ? f2(cj[5].z, cj[5].w) : f2(cj[5].x, cj[5].y);
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) {
-            float2 dx = __ffma2_rn(xj, neg1, xi[a][0]), dy = __ffma2_rn(yj, neg1, xi[a][1]), dz = __ffma2_rn(zj, neg1, xi[a][2]);
+            float2 dx = isub(xj, xi[a][0]), dy = isub(yj, xi[a][1]), dz = isub(zj, xi[a][2]);
             float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
             // WF: (hRi, sei) = (a_i, b_i), (hj, sj) = (a_j, b_j); e12 holds w_ij
-            float2 e12 = WF ? __ffma2_rn(sei[a], hj, __fmul2_rn(hRi[a], sj)) : __fmul2_rn(sei[a], sj);
-            float2 qq = __fmul2_rn(xi[a][3], qj);
-            float2 Rij = WF ? e12 : __ffma2_rn(hRi[a], one, hj);   // add.f32x2 is lowered to two FADDs; FFMA2 by one stays packed
+            float2 e12 = WF ? ifma(sei[a], hj, imul(hRi[a], sj)) : imul(sei[a], sj);
+            float2 qq = imul(xi[a][3], qj);
+            float2 Rij = WF ? e12 : iadd(hRi[a], hj);
             if (MASKED) {
                 const bool on0 = (m16 >> (4 * a + 2 * p)) & 1u, on1 = (m16 >> (4 * a + 2 * p + 1)) & 1u;
                 r2.x = on0 ? r2.x : NB_MASKED_R2; r2.y = on1 ? r2.y : NB_MASKED_R2;
@@ -781,7 +822,7 @@ __device__ __forceinline__ bool nb_micro2(const float2 (&xi)[NB_NI][4], const fl
 #else
                 float2 s = __fmul2_rn(u, __fmul2_rn(inv, inv));
 #endif
-                Fi[a][0] = __ffma2_rn(s, dx, Fi[a][0]); Fi[a][1] = __ffma2_rn(s, dy, Fi[a][1]); Fi[a][2] = __ffma2_rn(s, dz, Fi[a][2]);
+                facc(Fi[a][0], s, dx); facc(Fi[a][1], s, dy); facc(Fi[a][2], s, dz);
                 Fj[p][0] = __ffma2_rn(s, dx, Fj[p][0]); Fj[p][1] = __ffma2_rn(s, dy, Fj[p][1]); Fj[p][2] = __ffma2_rn(s, dz, Fj[p][2]);
             }
         }
@@ -800,9 +841,9 @@ __device__ __forceinline__ float ex2_fast(float x) {
 }
 
 template <bool GRAD, bool MASKED, bool FULL>
-__device__ __forceinline__ bool nb_micro2_exact(const float2 (&xi)[NB_NI][4], const float2 (&hRi)[NB_NI], const float2 (&sei)[NB_NI],
+__device__ __forceinline__ bool nb_micro2_exact(const ival (&xi)[NB_NI][4], const ival (&hRi)[NB_NI], const ival (&sei)[NB_NI],
                                                  const float4 (&cj)[6], uint32_t m16,
-                                                 float2 (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
+                                                 fval (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
     constexpr bool WF = NB_WFORM && !FULL;
     constexpr float LOG2E = 1.4426950408889634f;
     float rmin = 3.0e38f;
@@ -817,11 +858,11 @@ __device__ __forceinline__ bool nb_micro2_exact(const float2 (&xi)[NB_NI][4], co
         const float2 sj = p ? f2(cj[5].z, cj[5].w) : f2(cj[5].x, cj[5].y);
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) {
-            float2 dx = __ffma2_rn(xj, neg1, xi[a][0]), dy = __ffma2_rn(yj, neg1, xi[a][1]), dz = __ffma2_rn(zj, neg1, xi[a][2]);
+            float2 dx = isub(xj, xi[a][0]), dy = isub(yj, xi[a][1]), dz = isub(zj, xi[a][2]);
             float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-            float2 e12 = WF ? __ffma2_rn(sei[a], hj, __fmul2_rn(hRi[a], sj)) : __fmul2_rn(sei[a], sj);
-            float2 qq = __fmul2_rn(xi[a][3], qj);
-            float2 Rij = WF ? e12 : __ffma2_rn(hRi[a], one, hj);
+            float2 e12 = WF ? ifma(sei[a], hj, imul(hRi[a], sj)) : imul(sei[a], sj);
+            float2 qq = imul(xi[a][3], qj);
+            float2 Rij = WF ? e12 : iadd(hRi[a], hj);
             if (MASKED) {
                 const bool on0 = (m16 >> (4 * a + 2 * p)) & 1u, on1 = (m16 >> (4 * a + 2 * p + 1)) & 1u;
                 r2.x = on0 ? r2.x : NB_MASKED_R2; r2.y = on1 ? r2.y : NB_MASKED_R2;
@@ -862,7 +903,7 @@ __device__ __forceinline__ bool nb_micro2_exact(const float2 (&xi)[NB_NI][4], co
                 const float2 dw1 = f2(f1x ? 1.f : ex1.x, f1y ? 1.f : ex1.y), dw2 = f2(f2x ? 1.f : ex2.x, f2y ? 1.f : ex2.y);
                 const float2 gl = __fmul2_rn(__fmul2_rn(ulj, iw1), dw1), gc = __fmul2_rn(__fmul2_rn(ec, iw2), dw2);
                 const float2 sf = __fmul2_rn(__ffma2_rn(gl, one, gc), dinv);
-                Fi[a][0] = __ffma2_rn(sf, dx, Fi[a][0]); Fi[a][1] = __ffma2_rn(sf, dy, Fi[a][1]); Fi[a][2] = __ffma2_rn(sf, dz, Fi[a][2]);
+                facc(Fi[a][0], sf, dx); facc(Fi[a][1], sf, dy); facc(Fi[a][2], sf, dz);
                 Fj[p][0] = __ffma2_rn(sf, dx, Fj[p][0]); Fj[p][1] = __ffma2_rn(sf, dy, Fj[p][1]); Fj[p][2] = __ffma2_rn(sf, dz, Fj[p][2]);
             }
         }
@@ -888,14 +929,15 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     const float* xb = x + (long)b * sxb;
     const bool masked = IJ.z >= 0;
 
-    float2 xi[NB_NI][4], hRi[NB_NI], sei[NB_NI], Fi[NB_NI][3];
+    ival xi[NB_NI][4], hRi[NB_NI], sei[NB_NI];
+    fval Fi[NB_NI][3];
 #pragma unroll
     for (int a = 0; a < NB_NI; ++a) {
         const float4 v = nb_load_atom(xb, sxc, sxn, q, i0 + 4 * lane + a, N);
         const float2 pr = par[i0 + 4 * lane + a];
-        xi[a][0] = dup(v.x); xi[a][1] = dup(v.y); xi[a][2] = dup(v.z); xi[a][3] = dup(v.w);
-        hRi[a] = dup(pr.x); sei[a] = dup(pr.y);
-        Fi[a][0] = Fi[a][1] = Fi[a][2] = dup(0.f);
+        xi[a][0] = imake(v.x); xi[a][1] = imake(v.y); xi[a][2] = imake(v.z); xi[a][3] = imake(v.w);
+        hRi[a] = imake(pr.x); sei[a] = imake(pr.y);
+        Fi[a][0] = Fi[a][1] = Fi[a][2] = fzero();
     }
     {
         float* sf = reinterpret_cast<float*>(s_j);
@@ -934,8 +976,8 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         float dSl = 0.f, dSc = 0.f;
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) {
-            ui[a] = make_float4(xi[a][0].x, xi[a][1].x, xi[a][2].x, xi[a][3].x);
-            upi[a] = make_float2(hRi[a].x, sei[a].x);
+            ui[a] = make_float4(ilo(xi[a][0]), ilo(xi[a][1]), ilo(xi[a][2]), ilo(xi[a][3]));
+            upi[a] = make_float2(ilo(hRi[a]), ilo(sei[a]));
             dFi[a] = make_float3(0.f, 0.f, 0.f);
         }
         const float* cf = reinterpret_cast<const float*>(cj);
@@ -947,7 +989,7 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         }
         nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
 #pragma unroll
-        for (int a = 0; a < NB_NI; ++a) { Fi[a][0].x += dFi[a].x; Fi[a][1].x += dFi[a].y; Fi[a][2].x += dFi[a].z; }
+        for (int a = 0; a < NB_NI; ++a) { faddlo(Fi[a][0], dFi[a].x); faddlo(Fi[a][1], dFi[a].y); faddlo(Fi[a][2], dFi[a].z); }
         Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
         Fj[0][0].y += dFj[1].x; Fj[0][1].y += dFj[1].y; Fj[0][2].y += dFj[1].z;
         Fj[1][0].x += dFj[2].x; Fj[1][1].x += dFj[2].y; Fj[1][2].x += dFj[2].z;
@@ -1000,7 +1042,7 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             reinterpret_cast<float4*>(out + c * NB_T)[lane] =
-                make_float4(-(Fi[0][c].x + Fi[0][c].y), -(Fi[1][c].x + Fi[1][c].y), -(Fi[2][c].x + Fi[2][c].y), -(Fi[3][c].x + Fi[3][c].y));
+                make_float4(-fsum(Fi[0][c]), -fsum(Fi[1][c]), -fsum(Fi[2][c]), -fsum(Fi[3][c]));
             reinterpret_cast<float4*>(out + (3 + c) * NB_T)[gl] = make_float4(Fj[0][c].x, Fj[0][c].y, Fj[1][c].x, Fj[1][c].y);
         }
     }

@@ -499,6 +499,20 @@ int mlp_topology_pairs14(const mlp_topology* t, int32_t* pairs14) {
     return MLP_OK;
 }
 
+int mlp_topology_params14(const mlp_topology* t, float* vdw_14R, float* vdw_14e, float* q1q2_14) {
+    if (!t) { mlp_set_error("mlp_topology_params14: null topology"); return MLP_E_ARG; }
+    // utils.py:833-836, in the reference's fp32 tensor arithmetic: 0.5*(R_i+R_j), sqrt(e_i+e_j) (a SUM under the
+    // root, as written there), q_i*q_j/permittivity with permittivity = 1
+    const size_t n = t->pairs14.size() / 2;
+    for (size_t k = 0; k < n; ++k) {
+        const int i = t->pairs14[2 * k], j = t->pairs14[2 * k + 1];
+        if (vdw_14R) vdw_14R[k] = 0.5f * (t->vdw_R[i] + t->vdw_R[j]);
+        if (vdw_14e) vdw_14e[k] = std::sqrt(t->vdw_e[i] + t->vdw_e[j]);
+        if (q1q2_14) q1q2_14[k] = static_cast<float>(t->charges[i]) * static_cast<float>(t->charges[j]);
+    }
+    return MLP_OK;
+}
+
 int mlp_topology_atoms(const mlp_topology* t, char* names, char* resnames, char* types, double* charges,
                        float* vdw_R, float* vdw_eps) {
     if (!t) { mlp_set_error("mlp_topology_atoms: null topology"); return MLP_E_ARG; }

@@ -59,6 +59,9 @@ class Topology:
                                          _vp(self.exclusions)))
         self.bond_14_idxs = np.zeros((n14, 2), np.int32)
         _lib.check(L.mlp_topology_pairs14(self._h, _vp(self.bond_14_idxs)))
+        # 1-4 scaled parameters (utils.py:833-836; computed by the reference, used by no energy term)
+        self.vdw_14R, self.vdw_14e, self.q1q2_14 = (np.zeros(n14, np.float32) for _ in range(3))
+        _lib.check(L.mlp_topology_params14(self._h, _vp(self.vdw_14R), _vp(self.vdw_14e), _vp(self.q1q2_14)))
         nm, rn, ty = (np.zeros((n, 8), np.uint8) for _ in range(3))
         self.atom_charges = np.zeros(n, np.float64)
         self.atom_R = np.zeros(n, np.float32)

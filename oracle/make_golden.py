@@ -14,6 +14,8 @@ Files
   energy_<case>.npz         inputs x [B,N,3] f32 and, per term (bond, angle, torsion, nb):
                             fp32 reference batch values, fp64 per-conformation energies and
                             fp64 gradients
+  energy_full_<case>.npz    NB='full' (_cdist_nb_full): fp64 energies / gradients, the 1-4 pair list and the 1-4
+                            scaled parameter arrays (bbcb, pep28; ``--full-nb`` writes only these)
 Cases: bbcb (N,CA,CB,C,O -> 2145 atoms), heavy (all 3286), tile2 (two bbcb tiles as two
 chains, SURVEY 8d config 4 construction, 4288 -> 4286 atoms), pep28 (one residue of each of the 28
 amino12.lib templates with all hydrogens, 444 atoms, random-walk coordinates).
@@ -140,6 +142,53 @@ def energy_case(tag, obj, x_bn3, grad_frames):
     print(tag, "fp32 batch sums", out["ref32_batch_sums"], "fp64 sums", e64.sum(0))
 
 
+def full_nb_case(tag, info, x_bn3, grad_frames):
+    """``NB='full'`` (``_cdist_nb_full``, torch_protein_energy.py:224-230: adds the attractive -B/w^6 term) and the 1-4
+    scaled parameter arrays the reference computes but never uses (utils.py:833-836): fp64 per-conformation energies and
+    gradients from the unmodified reference -> energy_full_<tag>.npz (pins the oracle's ``full`` branch)."""
+    frame = torch.from_numpy(x_bn3[0].T.copy()).float()
+    obj, cap, _ = ref_loader.build_reference(frame, info, pair_exclusions=True, NB="full")
+    x32 = torch.from_numpy(x_bn3).permute(0, 2, 1).contiguous()
+    B = x32.shape[0]
+    out = dict(x=x_bn3.astype(np.float32))
+    xr = x32.clone().requires_grad_(True)
+    nb = obj._nb_loss(xr)
+    nb.backward()
+    out["ref32_batch_sum"] = np.float64(nb.item())
+    obj64 = ref_loader.to_double(obj)
+    e64 = np.zeros(B)
+    g64 = np.zeros((len(grad_frames), x_bn3.shape[1], 3))
+    for i in range(B):
+        xi = x32[i:i + 1].double().requires_grad_(True)
+        e = obj64._nb_loss(xi)
+        e64[i] = e.item()
+        if i in grad_frames:
+            (g,) = torch.autograd.grad(e, xi)
+            g64[grad_frames.index(i)] = g[0].T.numpy()
+    out["e64"], out["g64"], out["grad_frames"] = e64, g64, np.array(grad_frames, dtype=np.int64)
+    as64 = lambda v: np.asarray(v.double().numpy() if torch.is_tensor(v) else v, dtype=np.float64)
+    out["bond_14_idxs"] = np.asarray(cap["bond_14_idxs"], dtype=np.int64)
+    out["vdw_14R"], out["vdw_14e"], out["q1q2_14"] = as64(cap["vdw_14R"]), as64(cap["vdw_14e"]), as64(cap["q1q2_14"])
+    np.savez_compressed(os.path.join(OUT, f"energy_full_{tag}.npz"), **out)
+    print(tag, "NB=full fp32 batch sum", out["ref32_batch_sum"], "fp64 sum", e64.sum(), "n14", len(out["bond_14_idxs"]))
+
+
+def main_full():
+    """Round 2 additions; the files written by main() are left untouched."""
+    info, X = read_pdb_frames(os.path.join(ref_loader.REF, "test", "MurD_test.pdb"))
+    g = torch.Generator().manual_seed(20261020)
+    binfo, bX = select_atoms(info, X, BB)
+    noise = torch.randn(2, bX.shape[1], 3, generator=g).numpy().astype(np.float32)
+    xb = np.concatenate([bX[:3], bX[3:4] + 1.0 * noise[:1], bX[4:5] + 0.1 * noise[1:]])
+    full_nb_case("bbcb", binfo, xb, grad_frames=[0, 3, 4])
+    at, _, _, _ = topology_oracle.parse_forcefield(ref_loader.PARAM_DIR)
+    pinfo = np.array([(name, res, k + 1) for k, res in enumerate(at) for name in at[res]], dtype=object)
+    rng = np.random.default_rng(28)
+    walk = np.cumsum(rng.normal(scale=0.9, size=(len(pinfo), 3)), axis=0).astype(np.float32)
+    xp = np.stack([walk, walk * 1.5, walk * 0.6]).astype(np.float32)
+    full_nb_case("pep28", pinfo, xp, grad_frames=[0, 1, 2])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     info, X = read_pdb_frames(os.path.join(ref_loader.REF, "test", "MurD_test.pdb"))
@@ -186,4 +235,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--full-nb" in sys.argv:
+        main_full()
+    else:
+        main()
+        main_full()

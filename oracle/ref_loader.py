@@ -46,6 +46,7 @@ _CAPTURE_NAMES = (
     "bond_para", "angle_para", "torsion_para",
     "atom_names", "atom_charges", "atom_R", "atom_e",
     "bond_types", "angle_types", "torsion_types",
+    "vdw_14R", "vdw_14e", "q1q2_14",
 )
 
 

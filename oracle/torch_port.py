@@ -23,9 +23,12 @@ import torch
 
 
 class TorchCPUPort:
-    def __init__(self, topo: dict, dtype=torch.float32, nb_full: bool = False):
-        """topo: arrays named as in tests/golden/topo_*.npz (or ``Topology.as_dict()``)."""
+    def __init__(self, topo: dict, dtype=torch.float32, nb_full: bool = False, device="cpu"):
+        """topo: arrays named as in tests/golden/topo_*.npz (or ``Topology.as_dict()``).
+        ``device``: "cpu" (the timed CPU baseline) or a CUDA device - the same ATen op chain on the GPU, which is
+        what the reference itself runs with ``device='cuda'`` (bench.py's ``torch_cuda_baseline``)."""
         self.dtype = dtype
+        self.device = torch.device(device)
         self.nb_full = nb_full
         N = len(topo["atom_R"])
         self.N = N
@@ -74,6 +77,12 @@ class TorchCPUPort:
         self.vdw_A = (vdw_e * vdw_R ** 12).to(dtype)
         self.vdw_B = (2 * vdw_e * vdw_R ** 6).to(dtype)
         self.q1q2 = q1q2.to(dtype)
+        if self.device.type != "cpu":
+            mv = lambda t: t.to(self.device)
+            self.bond_groups = [(pat, [mv(r) for r in rows]) for pat, rows in self.bond_groups]
+            self.angle_groups = [(pat, [mv(r) for r in rows]) for pat, rows in self.angle_groups]
+            self.torsion_groups = [(pat, mv(row)) for pat, row in self.torsion_groups]
+            self.vdw_A, self.vdw_B, self.q1q2 = mv(self.vdw_A), mv(self.vdw_B), mv(self.q1q2)
 
     # x: [B,3,N]
     def bonded(self, x):
@@ -115,7 +124,7 @@ class TorchCPUPort:
 
     def energy_and_grad(self, x, nonbonded=True):
         """One forward + backward of the sum of all terms; returns ([4] batch sums, grad [B,3,N])."""
-        x = x.detach().to(self.dtype).requires_grad_(True)
+        x = x.detach().to(self.device, self.dtype).requires_grad_(True)
         terms = list(self.bonded(x))
         if nonbonded:
             terms.append(self.nonbonded(x))

@@ -176,10 +176,14 @@ def test_edge_batches(dev, energy_objs, golden_energy):
     big = x1.expand(37, 3, N)                                         # stride_b = 0 broadcast batch
     eb = tpe.energy_per_conformation(big)
     assert torch.allclose(eb, e1.expand(37, 4), rtol=1e-6)
-    with pytest.raises(AssertionError):
+    with pytest.raises(ValueError):
         tpe.energy_per_conformation(torch.zeros(1, 3, N + 1, device=dev))
     with pytest.raises(RuntimeError):
         tpe.energy_per_conformation(torch.zeros(1, 3, N))
+    with pytest.raises(TypeError):
+        tpe.energy_per_conformation(torch.zeros(1, 3, N, device=dev, dtype=torch.float64))
+    with pytest.raises(TypeError):
+        tpe.energy_and_gradient(torch.zeros(1, 3, N, device=dev, dtype=torch.float16))
 
 
 def test_nonfinite_inputs_stay_in_their_conformation(dev, energy_objs, golden_energy):
@@ -419,3 +423,59 @@ def test_alternative_code_paths_agree(knob, dev, golden_topo, golden_energy, mon
     for k, term in enumerate(TERMS):
         for q in range(len(gf)):
             assert rel(g[k, q], en["g64"][q, k]) < TOL, (knob, term, q)
+
+
+def test_full_lj_mode_vs_reference_vectors(dev, energy_objs):
+    """NB='full' against fp64 runs of the reference's own ``_cdist_nb_full`` (torch_protein_energy.py:224-230;
+    tests/golden/energy_full_*.npz, written by oracle/make_golden.py --full-nb)."""
+    from conftest import load_golden
+    for case in ("bbcb", "pep28"):
+        en = load_golden("energy_full_" + case)
+        tpe = energy_objs(case, "full")
+        gf = list(en["grad_frames"])
+        x = torch.from_numpy(en["x"]).to(dev).permute(0, 2, 1).requires_grad_(True)
+        e = tpe.energy_per_conformation(x)
+        e[:, 3].sum().backward()
+        got_e = e[:, 3].detach().double().cpu().numpy()
+        assert np.all(np.abs(got_e - en["e64"]) < TOL * np.abs(en["e64"])), (case, got_e, en["e64"])
+        got_g = x.grad.permute(0, 2, 1).double().cpu().numpy()
+        for q, f in enumerate(gf):
+            assert rel(got_g[f], en["g64"][q]) < TOL, (case, f, rel(got_g[f], en["g64"][q]))
+        # the reference's batch-sum call on the same object
+        assert abs(float(tpe._nb_loss(x.detach())) - en["e64"].sum()) < TOL * abs(en["e64"].sum())
+
+
+def test_zero_upstream_weight_stops_nonfinite_terms(dev, energy_objs, golden_topo, golden_energy):
+    """A term or a conformation the loss masked out (zero upstream gradient) must not reach dL/dx as NaN * 0:
+    (a) a conformation with a NaN coordinate and weight 0 gets an exactly zero gradient, the others their exact one;
+    (b) a conformation whose ANGLE term is NaN (coincident bonded atoms, finite coordinates) but whose loss only
+        uses bond + nb gets the finite bond + nb gradient (the trainer's nansum over the three bonded sums does this,
+        torch_physics_trainer.py:40-42)."""
+    topo = golden_topo("bbcb")
+    tpe = energy_objs("bbcb")
+    xs = golden_energy("bbcb")["x"][:3].copy()
+    xs[1, 100, 0] = np.nan
+    i, j = (int(v) for v in topo["bond_idxs"][700])
+    xs[2, j] = xs[2, i]
+    x = torch.from_numpy(xs).to(dev).permute(0, 2, 1).requires_grad_(True)
+    e = tpe.energy_per_conformation(x)
+    w = torch.tensor([[1.0, 1.0, 1.0, 1.0], [0.0, 0.0, 0.0, 0.0], [1.0, 0.0, 0.0, 1.0]], device=dev)
+    torch.nansum(e * w).backward()
+    g = x.grad.permute(0, 2, 1).double().cpu().numpy()
+    assert np.isfinite(g).all()
+    assert (g[1] == 0).all()
+    _, g0 = eo.energy_all(xs[0], topo)
+    assert rel(g[0], g0.sum(0)) < TOL
+    # the oracle's bond gradient carries its own 0/0 on the coincident pair (forward-mode duals of |v| at v = 0);
+    # autograd - and the kernel - give 0 there, so compare away from those two atoms
+    _, g2 = eo.energy_all(xs[2], topo)
+    want = g2[0] + g2[3]
+    keep = np.ones(len(want), bool)
+    keep[[i, j]] = False
+    assert np.isfinite(want[keep]).all() and rel(g[2][keep], want[keep]) < TOL
+    # the same through bonded-only energies and three separately weighted sums (the trainer's call)
+    x2 = torch.from_numpy(xs).to(dev).permute(0, 2, 1).requires_grad_(True)
+    b, a, t = tpe._roll_bond_angle_torsion_loss(x2)
+    assert torch.isnan(a)
+    torch.nansum(torch.stack([b, a, t])).backward()
+    assert torch.isfinite(x2.grad[[0, 2]]).all()

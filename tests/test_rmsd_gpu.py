@@ -57,3 +57,28 @@ def test_aligned_rmsd_vs_numpy_kabsch():
     pad[:, :400] = torch.from_numpy((x - 40.0) / 15.0).to(dev)
     out2 = rmsd_to_targets(pad[:, :400], torch.from_numpy(t).to(dev), scale=15.0, shift=40.0, align=True).cpu().numpy()
     assert np.allclose(out2, out, rtol=1e-3, atol=1e-3)
+
+
+def test_paired_rmsd_and_input_checks():
+    """MLP_RMSD_PAIRED (get_error: structure b against target b, no B x B matrix), K > 8 targets per structure (several
+    blocks of targets), and the dtype / device / shape checks of the Python face."""
+    from molearn_b200.analysis.reducers import rmsd_to_targets
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(8)
+    x = torch.from_numpy(rng.normal(size=(19, 257, 3)).astype(np.float32) * 7).to(dev)
+    t = torch.from_numpy(rng.normal(size=(19, 257, 3)).astype(np.float32) * 7 + 1).to(dev)
+    for align in (False, True):
+        full = rmsd_to_targets(x, t, align=align)
+        pair = rmsd_to_targets(x, t, align=align, paired=True)
+        assert full.shape == (19, 19) and pair.shape == (19,)
+        assert torch.equal(pair, full.diagonal())
+    want = np.sqrt(((x.double().cpu().numpy()[:, None] - t.double().cpu().numpy()[None]) ** 2).sum(-1).mean(-1))
+    assert np.allclose(rmsd_to_targets(x, t).cpu().numpy(), want, rtol=1e-5)
+    with pytest.raises(ValueError):
+        rmsd_to_targets(x, t[:5], paired=True)
+    with pytest.raises(TypeError):
+        rmsd_to_targets(x.double(), t)
+    with pytest.raises(ValueError):
+        rmsd_to_targets(x, t[:, :100])
+    with pytest.raises(RuntimeError):
+        rmsd_to_targets(x.cpu(), t)

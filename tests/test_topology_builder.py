@@ -45,6 +45,19 @@ def test_builder_bit_exact(case, golden_topo, param_dir):
     assert np.all(ex[:, 0] < ex[:, 1]) and len(np.unique(ex, axis=0)) == len(ex)
 
 
+@pytest.mark.parametrize("case14", ["bbcb", "pep28"])
+def test_scaled_14_parameters_bit_exact(case14, golden_topo, param_dir):
+    """utils.py:833-836: vdw_14R, vdw_14e (sum under the root, as written there), q1q2_14 - fp32, bit for bit."""
+    from conftest import load_golden
+    from molearn_b200 import Topology
+    g = load_golden("energy_full_" + case14)
+    t = Topology(atominfo_from(golden_topo(case14)), param_dir=param_dir)
+    assert np.array_equal(t.bond_14_idxs, g["bond_14_idxs"])
+    assert np.array_equal(t.vdw_14R, g["vdw_14R"].astype(np.float32))
+    assert np.array_equal(t.vdw_14e, g["vdw_14e"].astype(np.float32))
+    assert np.array_equal(t.q1q2_14, g["q1q2_14"].astype(np.float32))
+
+
 def test_builder_matches_python_oracle_on_edge_inputs(param_dir):
     """Ragged / unusual inputs the golden files do not hold: OXT, HIS variants, CHARMM names,
     hydrogens with fix_h, a single residue, an empty list."""
