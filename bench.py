@@ -13,12 +13,16 @@ One "step" = one batch of 64 conformations through the hot path.
   roofline  the dominant kernel (non-bonded pair kernel) against the FP32 FMA peak, plus the
             bonded kernel against the measured HBM bandwidth at a large batch (roofline_bonded)
   cpu_baseline / --impl reference
-            the PyTorch CPU port of the reference algorithm (oracle/torch_port.py) on the host
-            cores, on a bounded sample (8 of the 64 conformations)
+            the PyTorch CPU port of the reference algorithm (oracle/torch_port.py, pinned to the reference's own
+            vectors by tests/test_oracle_energy.py) on the host cores, on a bounded sample (8 of the 64 conformations)
+  torch_cuda_baseline
+            the same op chain (what the reference runs with device='cuda') on the same B200: conformations/s,
+            kernel launches per step and peak memory, next to the three launches of this library
 
 N > 1 (torchrun): the loss path is "replicas only"  - every rank runs its own batch
-of 64, value = total conformations / max-over-ranks time ("weak").  The latent-grid scan, which
-does shard, is reported in the "scan" object.
+of 64, value = total conformations / max-over-ranks time ("weak").  The latent-grid scans, which
+do shard, are reported in the "scan" (BASELINE config 3) and "config5_50k_scan" objects and, as short
+flat keys (scan_pts_s, scan_ms, scan_checksum, config5_pts_s, ...), at the END of the JSON line.
 """
 from __future__ import annotations
 
@@ -139,9 +143,11 @@ def run_reference(args, rank, world):
     --steps/--warmup run within a couple of minutes."""
     if rank != 0:
         return
-    from molearn_b200 import Topology
     info, frames = murd()
-    topo = Topology(info).as_dict()
+    # topology arrays as the reference itself produced them (tests/golden/topo_bbcb.npz, written by
+    # oracle/make_golden.py from the unmodified reference): this arm loads nothing of the product
+    topo = dict(np.load(os.path.join(ROOT, "tests", "golden", "topo_bbcb.npz")))
+    assert len(topo["atom_R"]) == len(info)
     from oracle.torch_port import TorchCPUPort
     torch.set_num_threads(os.cpu_count() or 1)
     port = TorchCPUPort(topo)
@@ -179,6 +185,59 @@ def workload_config(n_atoms):
 
 
 # ---------------------------------------------------------------------------------------------
+def rows_checksum(rows):
+    """fp64 sum of log1p|v| over every entry of the gathered score rows: equal rows give equal checksums, and the
+    collapsed decodes' 1e10-sized energies do not drown the rest (a plain sum would)."""
+    return float(torch.log1p(rows.double().abs()).sum())
+
+
+def recheck(ma, rows, n, **kw):
+    """Largest relative difference between the gathered rows of a sharded scan and the same grid points scored again
+    on THIS rank alone (n points spread over the whole grid, i.e. over every rank's block): the proof, on hardware,
+    that N ranks give the surfaces one rank gives."""
+    total = rows.shape[0]
+    idx = torch.linspace(0, total - 1, n).long().unique()
+    again = ma.scan_scores_at(idx, **kw).double()
+    ref = rows[idx].double()
+    return float(((again - ref).abs() / ref.abs().clamp_min(1e-30)).max()), int(len(idx))
+
+
+def torch_cuda_rate(topo_dict, x_bn3, dev, reps, nonbonded=True):
+    """The reference's op chain (oracle/torch_port.py: roll groups over [B,3,N] + dense cdist NB) on the SAME GPU -
+    what `TorchProteinEnergy(device='cuda')` of the reference runs.  fwd + bwd; CUDA events; kernel launches per step
+    from the torch profiler; peak memory from the caching allocator."""
+    from oracle.torch_port import TorchCPUPort
+    port = TorchCPUPort(topo_dict, device=dev)
+    x = x_bn3.permute(0, 2, 1).contiguous().to(dev)
+    for _ in range(2):
+        port.energy_and_grad(x, nonbonded=nonbonded)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        port.energy_and_grad(x, nonbonded=nonbonded)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peak = torch.cuda.max_memory_allocated(dev)
+    launches = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            port.energy_and_grad(x, nonbonded=nonbonded)
+            torch.cuda.synchronize()
+        launches = int(sum(ev.count for ev in prof.key_averages() if getattr(ev, "device_type", None) is not None
+                           and "cuda" in str(ev.device_type).lower()))
+    except Exception:
+        pass
+    del port
+    torch.cuda.empty_cache()
+    return {"value": x.shape[0] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": int(x.shape[0]),
+            "kernel_launches_per_step": launches, "peak_memory_bytes": int(peak), "kind": "port",
+            "what": "PyTorch port of the reference op chain (roll + cdist) on this GPU, fwd+bwd, fp32"}
+
+
 def run_scan(dev, rank, world, info, frames, G, barrier):
     """MurD latent-grid scan GxG: decode (FoldingNet, cuDNN) + 4 energy terms + RMSD to the 16 dataset
     frames per point, through MolearnAnalysis.scan_scores; grid points sharded over the ranks and
@@ -211,6 +270,32 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+    checksum = rows_checksum(rows)
+    rc_rel, rc_n = recheck(ma, rows, 256, targets=targets)
+    fp32_decode = None
+    if world == 1:
+        # the same scan with cuDNN's TF32 convolution math switched off (fp32 decode): time and distance of the surfaces
+        old_tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            ma.setup_grid(samples=warm, padding=0.1)
+            ma.scan_scores(targets=targets)
+            ma.setup_grid(samples=G, padding=0.1)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            rows32 = ma.scan_scores(targets=targets)
+            f1.record()
+            torch.cuda.synchronize()
+        finally:
+            torch.backends.cudnn.allow_tf32 = old_tf32
+        d = ((rows.double() - rows32.double()).abs() / rows32.double().abs().clamp_min(1e-30))
+        fp32_decode = {"value": G * G / (f0.elapsed_time(f1) * 1e-3), "unit": "points/s", "ms": f0.elapsed_time(f1),
+                       "checksum": rows_checksum(rows32),
+                       "tf32_vs_fp32_rel_median": {"energy": float(d[:, :4].median()), "rmsd": float(d[:, 4:].median())},
+                       "tf32_vs_fp32_rel_max": {"energy": float(d[:, :4].max()), "rmsd": float(d[:, 4:].max())},
+                       "note": "the headline scan decodes with torch's default TF32 convolution math (the reference's decode does "
+                               "too); the kernels' parity is checked on the decoded structures themselves (tests/test_scan_gpu.py)"}
     plain = None
     if world == 1:
         # the same scan decoding through network.decode as the reference writes it (Conv1d -> BatchNorm1d -> ReLU, NCHW)
@@ -267,6 +352,7 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
                "sample": f"16 of the {G * G} grid points: CPU decode + PyTorch CPU port energy (forward) + NumPy-style RMSD, {c1:.2f} s"}
     return {"metric": "latent-grid points/sec (MurD, decode + 4 energy terms + RMSD to 16 frames)", "grid": G, "cpu_baseline": cpu,
             "value": G * G / (ms * 1e-3), "unit": "points/s", "ms": ms, "scaling": "strong", "n_gpus": world,
+            "checksum": checksum, "recheck_max_rel": rc_rel, "recheck_points": rc_n, "fp32_decode": fp32_decode,
             "columns": int(rows.shape[1]), "gather_bytes": ma.scan_stats["gather_bytes"],
             "points_this_rank": ma.scan_stats["points_this_rank"],
             "energy_rmsd_kernels_ms_this_rank": score_ms, "energy_rmsd_share": score_ms / ms,
@@ -276,14 +362,15 @@ def run_scan(dev, rank, world, info, frames, G, barrier):
             "wall_s": time.perf_counter() - t0}
 
 
-def run_config5(dev, rank, world, info, frames, barrier, G=None):
+def run_config5(dev, rank, world, info, frames, barrier, G, cpu_baseline=False):
     """BASELINE config 5: 24 MurD tiles on a 3x3x3 lattice (N = 51 432), FoldingNet decoder of that size,
-    setup_grid(128, bounds=(-1,1,-1,1)), 4 energy terms per point, sharded + gathered."""
+    setup_grid(G, bounds=(-1,1,-1,1)), 4 energy terms per point, sharded + gathered.  G = 128 on 8 GPUs (the
+    configuration BASELINE.json names); fewer GPUs run a smaller grid of the same system so that the default bench
+    stays within minutes."""
     import torch.distributed as dist
     from molearn_b200.analysis import MolearnAnalysis
     from molearn_b200.data import CoordinateSet, tile_system
     from molearn_b200.models import AutoEncoder
-    G = G or int(os.environ.get("MLP_CONFIG5_GRID", 128))
     tinfo, x = tile_system(info, frames, 24, batch=1)
     data = CoordinateSet(tinfo, x).prepare_dataset()
     torch.manual_seed(0)
@@ -305,9 +392,47 @@ def run_config5(dev, rank, world, info, frames, barrier, G=None):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+    rc_rel, rc_n = recheck(ma, rows, 16)
+    dv = ma.physics()._dev()
+    ws1 = int(_lib_ws(dv, 1))
+    cpu = None
+    if cpu_baseline and rank == 0 and world == 1:
+        # The reference cannot even be constructed at this size on the host (five dense [N,N] fp32 matrices = 53 GB,
+        # BASELINE.md row 5).  Scaled figure: CPU decode of ONE grid point with the full-size network (measured) + the
+        # PyTorch CPU port's energy (forward) at 2 tiles (N = 4286), scaled by (N/4286)^2 - stated as scaled.
+        from oracle.torch_port import TorchCPUPort
+        torch.set_num_threads(os.cpu_count() or 1)
+        net_cpu = AutoEncoder(out_points=x.shape[1])
+        net_cpu.load_state_dict(net.state_dict())
+        net_cpu.eval()
+        z1 = ma._encoded["grid"].reshape(-1, 2)[:1]
+        c0 = time.perf_counter()
+        with torch.no_grad():
+            net_cpu.decode(z1)
+        t_dec = time.perf_counter() - c0
+        sinfo, sx = tile_system(info, frames, 2, batch=1)
+        from molearn_b200 import Topology
+        port = TorchCPUPort(Topology(sinfo).as_dict())
+        xs = torch.from_numpy(sx).permute(0, 2, 1).contiguous()
+        with torch.no_grad():
+            port.bonded(xs); port.nonbonded(xs)
+            c0 = time.perf_counter()
+            port.bonded(xs); port.nonbonded(xs)
+            t_e = time.perf_counter() - c0
+        scale = (x.shape[1] / sx.shape[1]) ** 2
+        cpu = {"value": 1.0 / (t_dec + t_e * scale), "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port", "scaled": True,
+               "sample": f"1 grid point: CPU decode at N = {x.shape[1]} ({t_dec:.2f} s, measured) + CPU port energy forward at N = {sx.shape[1]} "
+                         f"({t_e:.3f} s) scaled x{scale:.0f} (N^2) - the reference cannot be built at this N (53 GB of dense tables)"}
     return {"n_atoms": int(x.shape[1]), "grid": G, "value": G * G / (ms * 1e-3), "unit": "points/s", "ms": ms,
             "n_gpus": world, "columns": int(rows.shape[1]), "gather_bytes": ma.scan_stats["gather_bytes"],
-            "finite_rows": int(torch.isfinite(rows).all(dim=1).sum()), "info": ma.physics()._dev().info()}
+            "checksum": rows_checksum(rows), "recheck_max_rel": rc_rel, "recheck_points": rc_n,
+            "finite_rows": int(torch.isfinite(rows).all(dim=1).sum()), "workspace_bytes_per_conformation": ws1,
+            "cpu_baseline": cpu, "info": dv.info()}
+
+
+def _lib_ws(dv, B):
+    from molearn_b200 import _lib
+    return _lib.lib().mlp_energy_workspace_bytes(dv._h, B, _lib.TERM_ALL, 1)
 
 
 def run_config2(dev, info, frames):
@@ -341,7 +466,25 @@ def run_config2(dev, info, frames):
     dv.profile(False)
     ms = e0.elapsed_time(e1) / K
     phys_ms = pr["bonded"][0] / K
+    # beside it: the physics loss of the same 32 decoded conformations in the reference's formulation (roll groups,
+    # bonded terms only, fwd + bwd: what torch_physics_trainer.py:24-45 calls) on this GPU and on the host cores
+    base = {}
+    if not getattr(run_config2, "skip_baseline", False):
+        gen = (tr._internal["generated"].detach() * tr.std + tr.mean).float()          # [32,N,3] Angstrom
+        topo = tr.physics_loss.topology.as_dict()
+        base["torch_cuda"] = torch_cuda_rate(topo, gen.cpu(), dev, reps=5, nonbonded=False)
+        from oracle.torch_port import TorchCPUPort
+        torch.set_num_threads(os.cpu_count() or 1)
+        port = TorchCPUPort(topo)
+        xc = gen.cpu().permute(0, 2, 1).contiguous()
+        port.energy_and_grad(xc, nonbonded=False)
+        c0 = time.perf_counter()
+        port.energy_and_grad(xc, nonbonded=False)
+        c1 = time.perf_counter() - c0
+        base["cpu"] = {"ms_per_step": 1e3 * c1, "cores": torch.get_num_threads(), "kind": "port",
+                       "sample": "bonded terms of the 32 generated conformations, fwd+bwd, PyTorch CPU port (roll formulation)"}
     return {"ms_per_step": ms, "batch": B, "physics_conformations": B // 2, "physics_kernels_ms_per_step": phys_ms,
+            "physics_loss_baselines": base,
             "physics_share": phys_ms / ms, "bonded_launches_per_step": pr["bonded"][1] / K,
             "loss": float(res["loss"]), "physics_loss": float(res["physics_loss"]),
             "note": "step time is dominated by the FoldingNet autoencoder (cuDNN); the physics loss is 2 launches"}
@@ -390,11 +533,89 @@ def run_config4(dev, info, frames, pk):
         del port
     except Exception as exc:                      # e.g. not enough host memory
         cpu = {"unavailable": str(exc)[:200]}
+    tc = None
+    if cpu is not None and "unavailable" not in cpu:
+        del g, e
+        torch.cuda.empty_cache()
+        try:   # the reference's dense [B,N,N] chain on this GPU: 0.46 GB per conformation and intermediate -> a batch of 8
+            tc = torch_cuda_rate(tpe.topology.as_dict(), torch.from_numpy(x[:8]), dev, reps=2)
+        except Exception as exc:
+            tc = {"unavailable": str(exc)[:200]}
     return {"n_atoms": tpe.n_atoms, "batch": BB, "conformations_per_s": BB / (ms * 1e-3), "ms_per_step": ms, "cpu_baseline": cpu,
+            "torch_cuda_baseline": tc, "workspace_bytes": int(_lib_ws(dv, BB)),
             "pairs_per_s": tpe.topology.n_nb_pairs * BB / (nb_ms * 1e-3), "nb_kernel_ms": nb_ms,
             "nb_fp32_frac": flops / (nb_ms * 1e-3) / 1e12 / peak, "bonded_kernel_ms": pr["bonded"][0] / pr["bonded"][1],
             "nb_reduce_ms": pr["nb_reduce"][0] / pr["nb_reduce"][1], "info": dv.info(),
-            "note": "input (16.5 MB) < L2; the NB kernel is FMA-bound, its traffic is the 1.4 GB partial-force scratch"}
+            "note": "input (16.5 MB) < L2; the NB kernel is FMA-bound, its memory traffic is the partial-force scratch (workspace_bytes)"}
+
+
+def run_heavy(dev, pk):
+    """All-heavy-atom MurD (N = 3286; the reference's worst case: 155 roll groups), batch 64, four terms +
+    gradient: whole-call rate and per-kernel times."""
+    from molearn_b200 import TorchProteinEnergy, _lib
+    d = np.load(os.path.join(ROOT, "tests", "golden", "murd_input.npz"))
+    info = np.empty((len(d["names"]), 3), dtype=object)
+    info[:, 0], info[:, 1], info[:, 2] = [str(a) for a in d["names"]], [str(a) for a in d["resnames"]], [int(r) for r in d["resids"]]
+    tpe = TorchProteinEnergy(None, info, device=dev)
+    dv = tpe._dev()
+    x = make_batch(np.ascontiguousarray(d["coords"]), 3).to(dev)
+    g = torch.empty_like(x)
+    e = torch.empty((B, 4), device=dev)
+    for _ in range(3):
+        dv.eval(x.permute(0, 2, 1), e, g.permute(0, 2, 1), None, _lib.TERM_ALL)
+    torch.cuda.synchronize()
+    K = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        dv.eval(x.permute(0, 2, 1), e, g.permute(0, 2, 1), None, _lib.TERM_ALL)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    dv.profile(True)
+    for _ in range(K):
+        dv.eval(x.permute(0, 2, 1), e, g.permute(0, 2, 1), None, _lib.TERM_ALL)
+    pr = dv.profile_read()
+    dv.profile(False)
+    nb_ms = pr["nb"][0] / pr["nb"][1]
+    peak = 148 * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    top = tpe.topology
+    return {"n_atoms": tpe.n_atoms, "batch": B, "conformations_per_s": B / (ms * 1e-3), "ms_per_step": ms,
+            "terms": {"bonds": len(top.bond_idxs), "angles": len(top.angle_idxs), "torsions": len(top.torsion_idxs)},
+            "nb_kernel_ms": nb_ms, "nb_fp32_frac": FLOPS_PER_PAIR * top.n_nb_pairs * B / (nb_ms * 1e-3) / 1e12 / peak,
+            "bonded_kernel_ms": pr["bonded"][0] / pr["bonded"][1], "nb_reduce_ms": pr["nb_reduce"][0] / pr["nb_reduce"][1],
+            "launches_per_step": 3, "info": dv.info()}
+
+
+def fp32_probe(dev):
+    """Live FP32 FMA-pipe peak of this GPU: the library's probe kernel (mlp_probe_fp32), FFMA and FFMA2, CUDA events."""
+    from molearn_b200 import _lib
+    L = _lib.lib()
+    n = L.mlp_probe_fp32(None, 0, 0, 1, None)
+    buf = torch.empty(n, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    out = {}
+    for packed, name in ((0, "ffma"), (1, "ffma2")):
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            flops = L.mlp_probe_fp32(buf.data_ptr(), n, packed, 20000, st)
+            e1.record()
+            torch.cuda.synchronize()
+            if flops > 0:
+                best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        out[name + "_tflops"] = best
+    return out
+
+
+def ncu_summary():
+    """Counters that only a profiler sees (DRAM bytes, pipe utilisation) come from the committed summary of the last
+    capture, with the commit it was taken at - never from constants in this file."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_summary.json")))
+    except Exception:
+        return {}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -408,8 +629,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip roofline_bonded / scan / large-N extras")
     ap.add_argument("--scan-grid", type=int, default=256, help="G of the GxG latent grid of the scan section")
     ap.add_argument("--bonded-only", action="store_true", help="tuning aid: only the headline + roofline_bonded sections")
-    ap.add_argument("--config5", action="store_true", help="also run BASELINE config 5 (51 432 atoms, 128x128 scan)")
-    ap.add_argument("--config5-grid", type=int, default=128)
+    ap.add_argument("--config5", action="store_true", help="run BASELINE config 5 (51 432-atom scan) even with --no-extras")
+    ap.add_argument("--config5-grid", type=int, default=0, help="G of the config-5 grid (default: 128 on 8 GPUs, 16*sqrt(N) below)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -608,8 +829,12 @@ def main():
     if not args.no_extras and not args.bonded_only:
         out["scan"] = run_scan(dev, rank, world, info, frames, args.scan_grid, barrier)
 
-    if args.config5:
-        out["config5_50k_scan"] = run_config5(dev, rank, world, info, frames, barrier)
+    # ---- BASELINE config 5 (51 432 atoms): the named 128 x 128 grid on 8 GPUs; the same system on a smaller grid
+    # with fewer GPUs, so that every default run exercises it ------------------------------------------------------
+    c5_grid = args.config5_grid or (128 if world >= 8 else 16 * max(1, int(round(np.sqrt(world)))))
+    if (not args.no_extras and not args.bonded_only) or args.config5:
+        out["config5_50k_scan"] = run_config5(dev, rank, world, info, frames, barrier, c5_grid,
+                                              cpu_baseline=not args.no_cpu_baseline)
 
     if rank == 0:
         # ---- per-kernel durations (CUDA events on the launching stream, inside the C ABI) ----
@@ -624,11 +849,14 @@ def main():
         fp32_peak = 148 * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12       # TFLOP/s, FMA pipe
         flops = FLOPS_PER_PAIR * top.n_nb_pairs * B
         ach = flops / (nb_ms * 1e-3) / 1e12
-        out["roofline"] = {"kernel": "nb_kernel2<grad> (packed FP32 pair kernel)", "bound": "fp32", "achieved": ach, "peak": fp32_peak,
+        ncu = ncu_summary()
+        probe = fp32_probe(dev)
+        out["roofline"] = {"kernel": "non-bonded pair kernel <grad> (packed FP32, FFMA2)", "bound": "fp32", "achieved": ach, "peak": fp32_peak,
                            "unit": "TFLOP/s", "frac": ach / fp32_peak,
-                           "traffic": 1787904, "traffic_source": "dram__bytes_read+write of one launch, profiles/r01_summary.txt (inputs are L2-resident)",
-                           "measured_ffma_peak_tflops": 71.2, "fma_pipe_busy_pct_ncu": 72.7,
-                           "peak_source": "148 SM x 128 FMA lanes x 2 x sm_max_mhz (FP32 pipe; no tensor cores on this path)",
+                           "traffic": ncu.get("nb", {}).get("dram_bytes"), "ncu": ncu.get("nb"), "ncu_capture_commit": ncu.get("commit"),
+                           "measured_fp32_peak": probe, "frac_of_measured_ffma2_peak": ach / probe["ffma2_tflops"] if probe.get("ffma2_tflops") else None,
+                           "peak_source": "148 SM x 128 FMA lanes x 2 x sm_max_mhz (FP32 pipe; no tensor cores on this path; MEASURED_PEAKS.json "
+                                          "holds no FP32 figure, so the nominal pipe rate is the denominator and the probe's live rate is beside it)",
                            "algorithmic_flops_per_launch": flops, "kernel_ms": nb_ms,
                            "share_of_step": nb_ms / (ms / args.steps),
                            "other_kernels_ms": {"bonded": bd_ms, "nb_reduce": red_ms},
@@ -650,20 +878,42 @@ def main():
             topo_bytes = len(top.bond_idxs) * 16 + len(top.angle_idxs) * 32 + len(top.torsion_idxs) * 64
             byts = 24 * N * BB + topo_bytes
             gbs = byts / (t_ms * 1e-3) / 1e9
+            nb_ncu = ncu.get("bonded", {})
             out["roofline_bonded"] = {"kernel": "bonded_kernel<grad>", "bound": "hbm", "batch": BB, "achieved": gbs,
                                       "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                                      "traffic": 169336832, "traffic_source": "dram__bytes_read+write of one launch at B=4096, profiles/r01_bonded_b4096.txt",
+                                      "traffic": nb_ncu.get("dram_bytes"), "ncu": nb_ncu or None, "ncu_capture_commit": ncu.get("commit"),
+                                      "issue_frac": (nb_ncu.get("issue_active_pct") or 0) / 100 or None,
+                                      "real_bound": "instruction issue / latency (see issue_frac: executed warp-instructions per issue slot, "
+                                                    "from the ncu capture); the HBM fraction is what the spec's accounting asks for",
                                       "algorithmic_bytes_per_launch": byts, "kernel_ms": t_ms,
                                       "conformations_per_s": BB / (t_ms * 1e-3)}
             del xb, gb, eb
         if world == 1 and not args.no_extras and not args.bonded_only:
+            run_config2.skip_baseline = args.no_cpu_baseline
             out["config2_training_step"] = run_config2(dev, info, frames)
             out["config4_10k_atoms"] = run_config4(dev, info, frames, pk)
+            out["murd_all_heavy_atoms"] = run_heavy(dev, pk)
         if world == 1 and not args.no_cpu_baseline:
             rate, sec, cores = cpu_port_rate(top.as_dict(), make_batch(frames, 0)[:CPU_SAMPLE], reps=5)
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"{CPU_SAMPLE} of the {B} conformations, fwd+bwd of all four terms, "
                                              f"median of 5 ({sec:.3f} s each), PyTorch CPU port of the reference (roll + cdist)"}
+            tc = torch_cuda_rate(top.as_dict(), make_batch(frames, 0), dev, reps=5)
+            tc["ours_over_torch_cuda"] = value / world / tc["value"]
+            tc["our_kernel_launches_per_step"] = int(launches // max(args.steps, 1))
+            out["torch_cuda_baseline"] = tc
+        # ---- short flat keys LAST: a tail of the line still carries every headline number -------------------
+        tailkeys = {"n_gpus": world, "value": value, "e2e_value": e2e["value"], "roofline_frac": out["roofline"]["frac"]}
+        if "scan" in out:
+            sc = out["scan"]
+            tailkeys.update(scan_pts_s=sc["value"], scan_ms=sc["ms"], scan_checksum=sc["checksum"], scan_recheck_max_rel=sc["recheck_max_rel"])
+        if "config5_50k_scan" in out:
+            c5 = out["config5_50k_scan"]
+            tailkeys.update(config5_pts_s=c5["value"], config5_ms=c5["ms"], config5_grid=c5["grid"], config5_checksum=c5["checksum"],
+                            config5_recheck_max_rel=c5["recheck_max_rel"])
+        if "torch_cuda_baseline" in out:
+            tailkeys["ours_over_torch_cuda"] = out["torch_cuda_baseline"]["ours_over_torch_cuda"]
+        out["summary"] = tailkeys
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

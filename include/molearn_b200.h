@@ -216,6 +216,12 @@ int mlp_geometry_eval(const float* x, int64_t B, int64_t sxb, int64_t sxc, int64
                       const int32_t* pairs, const int32_t* pair_group, int64_t n_pairs, int64_t n_groups,
                       const int32_t* quads, int64_t n_quads, float* out, void* stream);
 
+/* Measurement aid (bench.py): one launch of a pure FP32 FMA loop - FFMA (packed = 0) or FFMA2 / fma.rn.f32x2
+ * (packed = 1) - on `stream`; the caller times it with events.  Returns the flops of the launch (> 0), or, when
+ * scratch is NULL, the number of floats of device scratch it needs; negative = error.  The non-bonded roofline's
+ * "measured FP32 peak" is this number, next to the nominal 148 SM x 128 lanes x 2 x clock. */
+int64_t mlp_probe_fp32(float* scratch, int64_t scratch_floats, int packed, int iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -330,10 +330,7 @@ class MolearnAnalysis:
             self.surfaces[z_key] = self._surface(rows[:, 1])
         return self.surfaces[s_key], self.surfaces[z_key], self.xvals, self.yvals
 
-    def scan_scores(self, targets=None, NB="repulsive"):
-        """One fused pass producing every device-side score row: 4 energy terms and, if ``targets``
-        ([K,N,3] Angstrom) is given, the RMSD to each target.  Returns a host ``[G^2, 4+K]`` tensor
-        (BASELINE config 3: decode + energy + RMSD to dataset)."""
+    def _score_fn(self, targets, NB):
         tpe = self.physics(NB)
         tg = None if targets is None else targets.to(self.device).float()
         k = 0 if tg is None else tg.shape[0]
@@ -342,7 +339,30 @@ class MolearnAnalysis:
             e = tpe.energy_per_conformation((dec * self.stdval + self.meanval).permute(0, 2, 1))
             return e if tg is None else torch.cat([e, rmsd_to_targets(dec, tg, self.stdval, self.meanval)], dim=1)
 
-        return self._scan_rows(4 + k, score)
+        return score, 4 + k
+
+    def scan_scores(self, targets=None, NB="repulsive"):
+        """One fused pass producing every device-side score row: 4 energy terms and, if ``targets``
+        ([K,N,3] Angstrom) is given, the RMSD to each target.  Returns a host ``[G^2, 4+K]`` tensor
+        (BASELINE config 3: decode + energy + RMSD to dataset)."""
+        score, n_cols = self._score_fn(targets, NB)
+        return self._scan_rows(n_cols, score)
+
+    def scan_scores_at(self, indices, targets=None, NB="repulsive"):
+        """The rows ``scan_scores`` produces for the grid points ``indices`` (flattened grid order), computed on THIS
+        rank only, no collective: re-scoring a few points, and the check that a sharded scan reproduces the
+        single-rank surfaces (bench.py).  Returns a host ``[len(indices), 4+K]`` tensor."""
+        if "grid" not in self._encoded:
+            raise ValueError("Call MolearnAnalysis.setup_grid before scanning")
+        score, n_cols = self._score_fn(targets, NB)
+        self._refresh_fused()
+        grid = self._encoded["grid"]
+        z_all = grid.reshape(grid.shape[0], -1)[torch.as_tensor(indices, dtype=torch.long)].to(self.device)
+        rows = torch.empty((z_all.shape[0], n_cols), dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            for slc in self._slices(z_all.shape[0]):
+                rows[slc] = score(z_all[slc], self._decode(z_all[slc]))
+        return rows.cpu()
 
     # -- geometry reducers (analyser.py:340-473, 980-1014) --------------------------------------------------
     def _geometry(self):

@@ -1342,6 +1342,27 @@ geom_stats_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, flo
     }
 }
 
+// FP32 FMA-pipe probe (bench.py measures the pipe's live peak with it, next to the nominal 148 x 128 x 2 x f):
+// 8 independent chains of FFMA (packed = 0) or FFMA2 (packed = 1) per thread, 16 lane-FMAs per chain step.
+constexpr int PROBE_BLOCKS = 148 * 8, PROBE_THREADS = 256;
+template <int PACKED>
+__global__ void __launch_bounds__(PROBE_THREADS) fp32_probe_kernel(float* __restrict__ out, int iters) {
+    float2 a[8], b = make_float2(1.0001f, 0.9999f), c = make_float2(0.5f, 0.25f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (PACKED) a[i] = __ffma2_rn(a[i], b, c);
+            else { a[i].x = fmaf(a[i].x, b.x, c.x); a[i].y = fmaf(a[i].y, b.y, c.y); }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y;
+    out[blockIdx.x * PROBE_THREADS + threadIdx.x] = s;
+}
+
 // ------------------------------------------------------------------------------------------
 // host: packing
 // ------------------------------------------------------------------------------------------
@@ -2011,6 +2032,18 @@ int mlp_rmsd_eval(const float* x, int64_t B, int64_t N, int64_t sxb, int64_t sxc
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { mlp_set_error(std::string("rmsd kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
     return MLP_OK;
+}
+
+int64_t mlp_probe_fp32(float* scratch, int64_t scratch_floats, int packed, int iters, void* stream_) {
+    const int64_t need = (int64_t)PROBE_BLOCKS * PROBE_THREADS;
+    if (!scratch) return need;                                  // size query
+    if (scratch_floats < need || iters <= 0) { mlp_set_error("mlp_probe_fp32: scratch too small / bad iteration count"); return MLP_E_ARG; }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (packed) fp32_probe_kernel<1><<<PROBE_BLOCKS, PROBE_THREADS, 0, stream>>>(scratch, iters);
+    else fp32_probe_kernel<0><<<PROBE_BLOCKS, PROBE_THREADS, 0, stream>>>(scratch, iters);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { mlp_set_error(std::string("probe kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
+    return 2LL * 16 * (int64_t)iters * need;                    // flops of the launch
 }
 
 int mlp_geometry_eval(const float* x, int64_t B, int64_t sxb, int64_t sxc, int64_t sxn, float scale,

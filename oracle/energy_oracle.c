@@ -141,29 +141,59 @@ double oracle_nonbonded(int32_t N, const double* x, const double* R, const doubl
                         int32_t ne, const int32_t* excl, int32_t full, double* g) {
     double E = 0.0;
     if (g) memset(g, 0, sizeof(double) * 3 * (size_t)N);
-    int32_t ep = 0;
-    for (int32_t i = 0; i < N; ++i) {
-        for (int32_t j = i + 1; j < N; ++j) {
-            while (ep < ne && (excl[2 * ep] < i || (excl[2 * ep] == i && excl[2 * ep + 1] < j))) ++ep;
-            if (ep < ne && excl[2 * ep] == i && excl[2 * ep + 1] == j) continue;
-            double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
-            double d = sqrt(dx * dx + dy * dy + dz * dz);
-            double Rij = 0.5 * fabs(R[i] + R[j]), eij = sqrt(eps[i] * eps[j]);
-            double R6 = Rij * Rij * Rij; R6 *= R6;
-            double A = eij * R6 * R6, Bc = 2.0 * eij * R6, qq = q[i] * q[j];
-            double dw1, dw2;
-            double w1 = warp(d, 1.9, &dw1), w2 = warp(d, 0.4, &dw2);
-            double i6 = 1.0 / (w1 * w1 * w1 * w1 * w1 * w1);
-            double elj = A * i6 * i6 - (full ? Bc * i6 : 0.0);
-            E += elj + qq / w2;
-            if (g && d > 0.0) {
-                double dE = (-12.0 * A * i6 * i6 + (full ? 6.0 * Bc * i6 : 0.0)) / w1 * dw1 - qq / (w2 * w2) * dw2;
-                double s = dE / d;
-                g[3 * i] += s * dx; g[3 * i + 1] += s * dy; g[3 * i + 2] += s * dz;
-                g[3 * j] -= s * dx; g[3 * j + 1] -= s * dy; g[3 * j + 2] -= s * dz;
-            }
+    /* first exclusion of every row (the list is sorted by i, then j): rows can then be evaluated independently */
+    int32_t* row = (int32_t*)malloc(sizeof(int32_t) * ((size_t)N + 1));
+    {
+        int32_t ep = 0;
+        for (int32_t i = 0; i <= N; ++i) {
+            while (ep < ne && excl[2 * ep] < i) ++ep;
+            row[i] = ep;
         }
     }
+    /* rows are spread over the host threads (OpenMP when compiled with it); every thread keeps its own energy and
+     * gradient accumulators, added in thread order at the end (fp64: the order is immaterial at the 1e-13 level) */
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        double El = 0.0;
+        double* gl = g ? (double*)calloc(3 * (size_t)N, sizeof(double)) : NULL;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 8) nowait
+#endif
+        for (int32_t i = 0; i < N; ++i) {
+            int32_t ep = row[i];
+            for (int32_t j = i + 1; j < N; ++j) {
+                while (ep < row[i + 1] && excl[2 * ep + 1] < j) ++ep;
+                if (ep < row[i + 1] && excl[2 * ep + 1] == j) continue;
+                double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+                double d = sqrt(dx * dx + dy * dy + dz * dz);
+                double Rij = 0.5 * fabs(R[i] + R[j]), eij = sqrt(eps[i] * eps[j]);
+                double R6 = Rij * Rij * Rij; R6 *= R6;
+                double A = eij * R6 * R6, Bc = 2.0 * eij * R6, qq = q[i] * q[j];
+                double dw1, dw2;
+                double w1 = warp(d, 1.9, &dw1), w2 = warp(d, 0.4, &dw2);
+                double i6 = 1.0 / (w1 * w1 * w1 * w1 * w1 * w1);
+                double elj = A * i6 * i6 - (full ? Bc * i6 : 0.0);
+                El += elj + qq / w2;
+                if (gl && d > 0.0) {
+                    double dE = (-12.0 * A * i6 * i6 + (full ? 6.0 * Bc * i6 : 0.0)) / w1 * dw1 - qq / (w2 * w2) * dw2;
+                    double s = dE / d;
+                    gl[3 * i] += s * dx; gl[3 * i + 1] += s * dy; gl[3 * i + 2] += s * dz;
+                    gl[3 * j] -= s * dx; gl[3 * j + 1] -= s * dy; gl[3 * j + 2] -= s * dz;
+                }
+            }
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        {
+            E += El;
+            if (gl) for (size_t k = 0; k < 3 * (size_t)N; ++k) g[k] += gl[k];
+        }
+        free(gl);
+    }
+    free(row);
     return E;
 }
 

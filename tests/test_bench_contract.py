@@ -34,7 +34,7 @@ def test_oracle_is_only_used_by_checker_code():
                 assert not pat.search(open(os.path.join(base, f)).read()), os.path.join(base, f)
     src = open(os.path.join(ROOT, "bench.py")).read()
     for m in pat.finditer(src):
-        # every oracle import in bench.py sits inside a function whose name marks it as a CPU-baseline leg
+        # every oracle import in bench.py sits inside one of the baseline legs (CPU port, or the same port on the GPU)
         head = src[:m.start()]
         fn = re.findall(r"^def (\w+)\(", head, re.M)[-1]
-        assert fn in ("cpu_port_rate", "run_reference", "run_scan", "run_config4"), fn
+        assert fn in ("cpu_port_rate", "run_reference", "run_scan", "run_config2", "run_config4", "run_config5", "torch_cuda_rate"), fn

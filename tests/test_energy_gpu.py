@@ -479,3 +479,61 @@ def test_zero_upstream_weight_stops_nonfinite_terms(dev, energy_objs, golden_top
     assert torch.isnan(a)
     torch.nansum(torch.stack([b, a, t])).backward()
     assert torch.isfinite(x2.grad[[0, 2]]).all()
+
+
+# ---- BASELINE config 5: the 51 432-atom system (24 chains) ---------------------------------------------------------
+@pytest.fixture(scope="module")
+def system_51k(dev):
+    from molearn_b200 import TorchProteinEnergy
+    from molearn_b200.data import tile_system
+    g = load_golden_murd_bbcb()
+    tinfo, x = tile_system(g[0], g[1], 24, batch=1, noise=0.2, seed=9)
+    tpe = TorchProteinEnergy(None, tinfo, device=dev)
+    assert tpe.n_atoms == 51432
+    return tpe, tpe.topology.as_dict(), x
+
+
+def _check_51k(tpe, topo, xs, dev, tols, label):
+    xd = torch.from_numpy(xs).to(dev).permute(0, 2, 1).requires_grad_(True)
+    e = tpe.energy_per_conformation(xd)
+    e.nansum().backward()
+    got = e.detach().double().cpu().numpy()[0]
+    want_e, want_g = eo.energy_all(xs[0], topo)
+    for k, name in enumerate(TERMS):
+        if np.isnan(want_e[k]):
+            assert np.isnan(got[k]), (label, name, got[k])
+        else:
+            assert abs(got[k] - want_e[k]) <= tols[k] * abs(want_e[k]), (label, name, got[k], want_e[k], abs(got[k] - want_e[k]) / abs(want_e[k]))
+    return got, want_e, xd.grad.permute(0, 2, 1).double().cpu().numpy()[0], want_g
+
+
+def test_51k_atoms_md_like_vs_oracle(dev, system_51k):
+    """MD-like conformation of the config-5 system (0.2 A noise): every term and the total gradient <= 1e-5."""
+    tpe, topo, x = system_51k
+    got, want, g, wg = _check_51k(tpe, topo, x, dev, [TOL] * 4, "md-like")
+    assert rel(g, wg.sum(0)) < TOL
+
+
+def test_51k_atoms_collapsed_vs_oracle(dev, system_51k):
+    """A collapsed structure (the regime of an untrained decoder: everything within a few Angstrom, E_nb ~ 1e10, the
+    pair kernel's exact-only loop) WITHOUT coincident atoms: every term and the gradient <= 1e-5."""
+    tpe, topo, x = system_51k
+    rng = np.random.default_rng(51)
+    xs = ((x - x.mean(axis=1, keepdims=True)) * 0.15 + rng.normal(scale=0.25, size=x.shape)).astype(np.float32)
+    got, want, g, wg = _check_51k(tpe, topo, xs, dev, [TOL] * 4, "collapsed")
+    assert want[3] > 1e7
+    assert rel(g, wg.sum(0)) < TOL
+
+
+def test_51k_atoms_coincident_atoms_semantics(dev, system_51k):
+    """The same collapsed structure with three pairs of bonded atoms put on the same point (an untrained decoder emits
+    such duplicates): bond finite, angle NaN (0/0), torsion finite with phi = atan2(0, 0) = 0, non-bonded finite - the
+    per-term outcome of the reference's forward pass, here and in the oracle; the finite terms still agree."""
+    tpe, topo, x = system_51k
+    rng = np.random.default_rng(52)
+    xs = ((x - x.mean(axis=1, keepdims=True)) * 0.15 + rng.normal(scale=0.25, size=x.shape)).astype(np.float32)
+    for k in (100, 20000, 51000):
+        i, j = (int(v) for v in topo["bond_idxs"][k])
+        xs[0, j] = xs[0, i]
+    got, want, _, _ = _check_51k(tpe, topo, xs, dev, [TOL, TOL, 1e-4, TOL], "coincident")
+    assert np.isfinite(got[0]) and np.isnan(got[1]) and np.isfinite(got[2]) and np.isfinite(got[3])

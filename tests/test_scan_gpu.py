@@ -26,11 +26,9 @@ def analysis(murd_data):
     from molearn_b200.models import AutoEncoder
     torch.manual_seed(0)
     net = AutoEncoder(out_points=murd_data.dataset.shape[1]).to("cuda:0")
-    # one decode batch = the whole 6x6 grid, and no TF32: decoding the same points in a different
-    # batch (or with a different cuDNN algorithm) moves the random-init network's collapsed,
-    # ill-conditioned structures by more than the energy tolerance
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    # torch's default convolution math (TF32 on), as bench.py's scans run.  One decode batch = the whole 6x6 grid, so
+    # the test's own decode of the grid reproduces the structures the scan scored (same kernels, same batch); the
+    # kernels are then checked on exactly those structures.
     ma = MolearnAnalysis(batch_size=36)
     ma.set_network(net)
     ma.set_dataset("train", murd_data)
@@ -50,12 +48,49 @@ def test_scan_physics_vs_oracle(analysis):
     assert total.shape == (6, 6) and len(xv) == 6 and len(yv) == 6
     topo = load_golden("topo_bbcb")
     dec = decoded_angstrom(ma)
-    for p in (0, 17, 35):
+    for p in range(36):                                                  # every grid point
         want, _ = eo.energy_all(dec[p], topo, want_grad=False)
         got = [ma.surfaces[f"Physics_{n}"].reshape(-1)[p] for n in ("bond", "angle", "torsion", "nb")]
         for k in range(4):
-            assert abs(got[k] - want[k]) < 2e-5 * abs(want[k]), (p, k, got[k], want[k])   # decode runs twice (TF32 noise aside: same kernels)
+            assert abs(got[k] - want[k]) < 2e-5 * abs(want[k]), (p, k, got[k], want[k])   # the oracle sees the fp32 structure of a second, identical decode
         assert abs(total.reshape(-1)[p] - want.sum()) < 2e-5 * abs(want.sum())
+
+
+def test_scan_physics_fp32_decode_vs_oracle(analysis):
+    """The same check with cuDNN's TF32 convolution math off (fp32 decode), all 36 points."""
+    ma = analysis
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for k in list(ma.surfaces):
+            if k.startswith("Physics"):
+                del ma.surfaces[k]
+        total, _, _ = ma.scan_physics()
+        topo = load_golden("topo_bbcb")
+        dec = decoded_angstrom(ma)
+        for p in range(36):
+            want, _ = eo.energy_all(dec[p], topo, want_grad=False)
+            got = [ma.surfaces[f"Physics_{n}"].reshape(-1)[p] for n in ("bond", "angle", "torsion", "nb")]
+            for k in range(4):
+                assert abs(got[k] - want[k]) < 2e-5 * abs(want[k]), (p, k, got[k], want[k])
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+        for k in list(ma.surfaces):
+            if k.startswith("Physics"):
+                del ma.surfaces[k]
+        ma.scan_physics()                                               # restore the TF32 surfaces the later tests compare with
+
+
+def test_scan_scores_at_matches_scan(analysis, murd_data):
+    """Re-scoring chosen grid points on one rank (scan_scores_at: bench.py's sharded-vs-single check) gives the rows of
+    the full scan."""
+    ma = analysis
+    tg = torch.from_numpy(murd_data.coords[:2])
+    rows = ma.scan_scores(targets=tg)
+    idx = [0, 7, 20, 35]
+    again = ma.scan_scores_at(idx, targets=tg)
+    assert again.shape == (4, 6)
+    assert torch.allclose(again, rows[idx], rtol=2e-4), (again - rows[idx]).abs().max()     # another batch shape: cuDNN may pick another kernel
 
 
 def test_scan_error_from_target(analysis, murd_data):
