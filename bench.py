@@ -188,7 +188,12 @@ def workload_config(n_atoms):
 def rows_checksum(rows):
     """fp64 sum of log1p|v| over every entry of the gathered score rows: equal rows give equal checksums, and the
     collapsed decodes' 1e10-sized energies do not drown the rest (a plain sum would)."""
-    return float(torch.log1p(rows.double().abs()).sum())
+    r = rows.double()
+    return float(torch.log1p(r.abs())[torch.isfinite(r)].sum())       # non-finite entries (0/0 angles of coincident atoms) are counted apart
+
+
+def rows_nonfinite(rows):
+    return int((~torch.isfinite(rows)).sum())
 
 
 def recheck(ma, rows, n, **kw):
@@ -199,7 +204,10 @@ def recheck(ma, rows, n, **kw):
     idx = torch.linspace(0, total - 1, n).long().unique()
     again = ma.scan_scores_at(idx, **kw).double()
     ref = rows[idx].double()
-    return float(((again - ref).abs() / ref.abs().clamp_min(1e-30)).max()), int(len(idx))
+    same_nan = torch.isfinite(again) == torch.isfinite(ref)
+    d = ((again - ref).abs() / ref.abs().clamp_min(1e-30))[torch.isfinite(ref) & torch.isfinite(again)]
+    worst = float(d.max()) if d.numel() else 0.0
+    return (worst if bool(same_nan.all()) else float("inf")), int(len(idx))
 
 
 def torch_cuda_rate(topo_dict, x_bn3, dev, reps, nonbonded=True):
@@ -425,7 +433,7 @@ def run_config5(dev, rank, world, info, frames, barrier, G, cpu_baseline=False):
                          f"({t_e:.3f} s) scaled x{scale:.0f} (N^2) - the reference cannot be built at this N (53 GB of dense tables)"}
     return {"n_atoms": int(x.shape[1]), "grid": G, "value": G * G / (ms * 1e-3), "unit": "points/s", "ms": ms,
             "n_gpus": world, "columns": int(rows.shape[1]), "gather_bytes": ma.scan_stats["gather_bytes"],
-            "checksum": rows_checksum(rows), "recheck_max_rel": rc_rel, "recheck_points": rc_n,
+            "checksum": rows_checksum(rows), "nonfinite_entries": rows_nonfinite(rows), "recheck_max_rel": rc_rel, "recheck_points": rc_n,
             "finite_rows": int(torch.isfinite(rows).all(dim=1).sum()), "workspace_bytes_per_conformation": ws1,
             "cpu_baseline": cpu, "info": dv.info()}
 
@@ -910,7 +918,7 @@ def main():
         if "config5_50k_scan" in out:
             c5 = out["config5_50k_scan"]
             tailkeys.update(config5_pts_s=c5["value"], config5_ms=c5["ms"], config5_grid=c5["grid"], config5_checksum=c5["checksum"],
-                            config5_recheck_max_rel=c5["recheck_max_rel"])
+                            config5_nonfinite=c5["nonfinite_entries"], config5_recheck_max_rel=c5["recheck_max_rel"])
         if "torch_cuda_baseline" in out:
             tailkeys["ours_over_torch_cuda"] = out["torch_cuda_baseline"]["ours_over_torch_cuda"]
         out["summary"] = tailkeys

@@ -45,6 +45,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -136,6 +137,7 @@ struct mlp_energy {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap = true;
+    bool nb_first = false;          // launch order of the two concurrent kernels (MLP_NB_FIRST)
     bool packed = NB_PACKED != 0;   // non-bonded pair loop in packed FP32 (FFMA2)
     // optional per-kernel timing (mlp_energy_profile): events on the launching stream
     bool profile = false;
@@ -1822,6 +1824,7 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
     if (rc == MLP_OK) rc = pack_nonbonded(E, *t);
     if (rc == MLP_OK) {
         if (const char* env = std::getenv("MLP_NO_OVERLAP")) E->overlap = std::atoi(env) == 0;
+        if (const char* env = std::getenv("MLP_NB_FIRST")) E->nb_first = std::atoi(env) != 0;
         if (const char* env = std::getenv("MLP_NB_PACKED")) E->packed = std::atoi(env) != 0;
         if (cudaStreamCreateWithFlags(&E->side, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -1830,11 +1833,21 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
         }
     }
     if (rc == MLP_OK) {
-        cudaError_t e1 = cudaFuncSetAttribute(bonded_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
-        cudaError_t e2 = cudaFuncSetAttribute(bonded_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
-        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(bonded_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
-        if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(bonded_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E->bonded_smem);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { mlp_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); rc = MLP_E_CUDA; }
+        // The opt-in dynamic shared-memory limit is a property of the kernel FUNCTION on a device, shared by every
+        // handle: it is only ever raised (a later, smaller topology must not lower it under an earlier handle).
+        static std::mutex mtx;
+        static std::map<int, size_t> raised;
+        std::lock_guard<std::mutex> lock(mtx);
+        size_t& have = raised[device];
+        if (E->bonded_smem > have) {
+            const int want = (int)E->bonded_smem;
+            cudaError_t err = cudaFuncSetAttribute(bonded_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+            if (err == cudaSuccess) err = cudaFuncSetAttribute(bonded_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+            if (err == cudaSuccess) err = cudaFuncSetAttribute(bonded_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+            if (err == cudaSuccess) err = cudaFuncSetAttribute(bonded_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+            if (err != cudaSuccess) { mlp_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err)); rc = MLP_E_CUDA; }
+            else have = E->bonded_smem;
+        }
     }
     cudaSetDevice(prev);
     if (rc != MLP_OK) { mlp_energy_destroy(E); return rc; }
@@ -1925,6 +1938,13 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
     } guard(e->device);
     CK(guard.enter());
+    cudaGetLastError();   // a stale (non-sticky) error left in this host thread by an earlier, unrelated runtime call is not ours to report
+    cudaError_t lerr = cudaSuccess;
+#define LAUNCH_CHECK(name)                                                                                    \
+    if ((lerr = cudaGetLastError()) != cudaSuccess) {                                                        \
+        mlp_set_error(std::string("launch of " name ": ") + cudaGetErrorString(lerr));                      \
+        return MLP_E_CUDA;                                                                                    \
+    }
     char* ws = static_cast<char*>(workspace);
     ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
     float* e_bonded = reinterpret_cast<float*>(ws + W.e_bonded);
@@ -1955,7 +1975,11 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
         bstream = e->side;
     }
-    if (bonded) {
+    // nb_first: the pair kernel is launched BEFORE the bonded kernel, so that the (short, latency-bound) bonded CTAs
+    // are handed out when the pair kernel's grid is exhausted - in its last, partially filled wave - instead of taking
+    // slots at the start.
+    const bool nb_first = fork && e->nb_first;
+    auto launch_bonded = [&]() {
         prof_begin(1);
         int cpc = (int)std::max<int64_t>(1, std::min<int64_t>(BONDED_CPC_MAX, (B * e->n_tiles) / (int64_t)(e->sm_count * 8)));
         dim3 grid(e->n_tiles, (unsigned)((B + cpc - 1) / cpc));
@@ -1967,10 +1991,15 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
 #undef BONDED_LAUNCH
         prof_end(1);
         ++launches;
+    };
+    auto bonded_checked = [&]() -> int { launch_bonded(); LAUNCH_CHECK("bonded_kernel"); return MLP_OK; };
+    if (bonded && !nb_first) {
+        if (int rc = bonded_checked()) return rc;
         if (fork) CK(cudaEventRecord(e->ev_join, e->side));
-    } else if (grad && !accumulate && !nonbonded) {
+    } else if (!bonded && grad && !accumulate && !nonbonded) {
         long n = (long)B * N * 3;
         zero_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad, sgb, sgc, sgn, N, (int)B);
+        LAUNCH_CHECK("zero_grad_kernel");
         ++launches;
     }
     if (nonbonded) {
@@ -1990,14 +2019,20 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         }
 #undef NB_LAUNCH2
 #undef NB_LAUNCH
+        LAUNCH_CHECK("the non-bonded pair kernel");
         prof_end(2);
         ++launches;
+        if (nb_first) {
+            if (int rc = bonded_checked()) return rc;
+            CK(cudaEventRecord(e->ev_join, e->side));
+        }
         if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient (and sums its energy partials)
         if (grad) {
             prof_begin(3);
             nb_reduce_kernel<<<dim3(e->n_nbt * (NB_T / 32), (unsigned)B), 32 * RED_PARTS, 0, stream>>>(fpart, e->d_red_off, e->d_red_list, e->n_pairs, N,
                 grad, sgb, sgc, sgn, weights, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0,
                 e_bonded, e->n_tiles, e_nb, energies, term_mask);
+            LAUNCH_CHECK("nb_reduce_kernel");
             prof_end(3);
             ++launches;
             energies_done = energies != nullptr;
@@ -2005,11 +2040,11 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     }
     if (energies && !energies_done) {
         finalize_kernel<<<(unsigned)B, 128, 0, stream>>>(e_bonded, e->n_tiles, e_nb, e->n_pairs, energies, term_mask);
+        LAUNCH_CHECK("finalize_kernel");
         ++launches;
     }
+#undef LAUNCH_CHECK
     e->last_launches = launches;
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) { mlp_set_error(std::string("kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
     return MLP_OK;
 }
 

@@ -87,10 +87,13 @@ def test_scan_scores_at_matches_scan(analysis, murd_data):
     ma = analysis
     tg = torch.from_numpy(murd_data.coords[:2])
     rows = ma.scan_scores(targets=tg)
-    idx = [0, 7, 20, 35]
+    # all 36 points in another order: the decode batch keeps its shape, so cuDNN runs the same kernels and every
+    # structure is reproduced bit for bit (a batch of another size may use another TF32 algorithm, and the energies of
+    # an untrained decoder's collapsed structures move by per cent under TF32-sized coordinate noise)
+    idx = torch.randperm(36, generator=torch.Generator().manual_seed(3))
     again = ma.scan_scores_at(idx, targets=tg)
-    assert again.shape == (4, 6)
-    assert torch.allclose(again, rows[idx], rtol=2e-4), (again - rows[idx]).abs().max()     # another batch shape: cuDNN may pick another kernel
+    assert again.shape == (36, 6)
+    assert torch.equal(again, rows[idx]), (again - rows[idx]).abs().max()
 
 
 def test_scan_error_from_target(analysis, murd_data):
