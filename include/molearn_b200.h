@@ -216,6 +216,18 @@ int mlp_geometry_eval(const float* x, int64_t B, int64_t sxb, int64_t sxc, int64
                       const int32_t* pairs, const int32_t* pair_group, int64_t n_pairs, int64_t n_groups,
                       const int32_t* quads, int64_t n_quads, float* out, void* stream);
 
+/* Internal coordinates of every structure over index lists: the device form of MolearnAnalysis.get_bondlengths /
+ * get_angles / get_dihedrals (analyser.py:418-566; formulas :791-861, the dihedral in its standard form).
+ *   x         dev [B,3,N] logical with strides; B <= 65535
+ *   pairs     dev [n_pairs,2]   -> distance |p0-p1| * scale
+ *   triples   dev [n_triples,3] -> angle p0-p1-p2 in radians
+ *   quads     dev [n_quads,4]   -> dihedral p0-p1-p2-p3 in radians (-pi, pi]
+ *   out       dev [B, n_pairs + n_triples + n_quads] fp32: distances, then angles, then dihedrals
+ */
+int mlp_internal_coords_eval(const float* x, int64_t B, int64_t sxb, int64_t sxc, int64_t sxn, float scale,
+                             const int32_t* pairs, int64_t n_pairs, const int32_t* triples, int64_t n_triples,
+                             const int32_t* quads, int64_t n_quads, float* out, void* stream);
+
 /* Measurement aid (bench.py): one launch of a pure FP32 FMA loop - FFMA (packed = 0) or FFMA2 / fma.rn.f32x2
  * (packed = 1) - on `stream`; the caller times it with events.  Returns the flops of the launch (> 0), or, when
  * scratch is NULL, the number of floats of device scratch it needs; negative = error.  The non-bonded roofline's

@@ -38,6 +38,8 @@ SYMBOLS = {
     "mlp_energy_profile_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mlp_geometry_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_int64,
                                   c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mlp_internal_coords_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64, c_void_p, c_int64,
+                                         c_void_p, c_int64, c_void_p, c_void_p]),
     "mlp_probe_fp32": (c_int64, [c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mlp_rmsd_eval": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_float,
                               c_void_p, c_int64, c_void_p, c_uint32, c_void_p]),

@@ -27,7 +27,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from .reducers import GeometryStats, backbone_indices, rmsd_to_targets
+from .reducers import GeometryStats, InternalCoords, backbone_indices, rmsd_to_targets
 
 
 @dataclass
@@ -372,49 +372,54 @@ class MolearnAnalysis:
             self._geom = GeometryStats(self._atominfo, self.device)
         return self._geom
 
-    def _structures(self, key):
-        """(dataset or None, decoded) in Angstrom on the device, like get_dataset/get_decoded(scale=True)."""
+    def _structure_batches(self, key):
+        """Yields ``(which, batch [b, n_atoms, 3] on the device in standardised units)`` for the dataset (if ``key`` names
+        one) and for its decoded counterpart - decoded on the device batch by batch, never staged on the host."""
         if key in self._datasets:
-            ds = self.get_dataset(key, scale=True)
-        elif key in self._encoded:
-            ds = None
-        else:
+            ds = self.get_dataset(key)
+            for slc in self._slices(ds.shape[0]):
+                yield "dataset", ds[slc].to(self.device).float()
+        elif key not in self._encoded:
             raise ValueError(f"Key {key} not found in _datasets or _encoded. Please load the dataset or setup a grid first.")
-        return ds, self.get_decoded(key, scale=True)
+        enc = self.get_encoded(key)
+        self._refresh_fused()
+        with torch.no_grad():
+            for slc in self._slices(enc.shape[0]):
+                yield "decoded", self._decode(enc[slc].reshape(enc[slc].shape[0], -1).to(self.device))
+
+    def _internal(self, key, groups, prefix, transpose):
+        """Evaluate the index groups on the device for dataset + decoded structures of ``key`` (Angstrom)."""
+        ic = InternalCoords(groups, self.device)
+        acc = {}
+        for which, batch in self._structure_batches(key):
+            vals = ic(batch, self.stdval)                                   # angles / dihedrals do not depend on scale or shift
+            for name, v in vals.items():
+                acc.setdefault(which, {}).setdefault(name, []).append(v.cpu())
+        out = {}
+        for which, d in acc.items():
+            out[f"{which}_{prefix}"] = {name: (torch.cat(v).numpy().T.copy() if transpose else torch.cat(v).numpy()).astype(np.float64)
+                                        for name, v in d.items()}
+        return out
 
     def get_bondlengths(self, key):
-        """Backbone bond lengths per bond and structure, ``{type: [n_bonds, F]}`` (analyser.py:418-473)."""
+        """Backbone bond lengths per bond and structure, ``{type: [n_bonds, F]}`` in Angstrom (analyser.py:418-473),
+        computed on the device (``mlp_internal_coords_eval``)."""
         bonds, _ = backbone_indices(self._atominfo)
-
-        def lengths(crds):
-            return {k: np.array([np.linalg.norm(crds[:, i, :] - crds[:, j, :], axis=1) for i, j in v]) for k, v in bonds.items()}
-
-        ds, dec = self._structures(key)
-        out = dict(decoded_bondlen=lengths(dec.numpy()))
-        if ds is not None:
-            out["dataset_bondlen"] = lengths(ds.numpy())
-        return out
+        return self._internal(key, {k: v for k, v in bonds.items() if len(v)}, "bondlen", transpose=True)
 
     def get_inversions(self, key):
         """Number of C-alpha chirality inversions per structure (analyser.py:340-416), computed on the device."""
         if not {"CA", "C", "N", "CB"}.issubset(set(str(a) for a in self._atominfo[:, 0])):
             raise ValueError("Atom selection should include CA, C, N, and CB")
         geom = self._geometry()
+        acc = {}
+        for which, batch in self._structure_batches(key):
+            acc.setdefault(which, []).append(geom(batch, self.stdval)[:, -1].cpu())      # the sign test is scale / shift invariant
+        return {f"{which}_inversions": torch.cat(v).numpy().astype(np.int64) for which, v in acc.items()}
 
-        def count(crds):
-            res = []
-            for slc in self._slices(crds.shape[0]):
-                res.append(geom(crds[slc].to(self.device).float())[:, -1].cpu())
-            return torch.cat(res).numpy().astype(np.int64)
-
-        ds, dec = self._structures(key)
-        out = dict(decoded_inversions=count(dec))
-        if ds is not None:
-            out["dataset_inversions"] = count(ds)
-        return out
-
-    # -- backbone angles / dihedrals of a dataset and its reconstruction (analyser.py:475-566; host-side NumPy:
-    #    these feed plots, not scans) ---------------------------------------------------------------------------
+    # -- backbone angles / dihedrals (analyser.py:475-566).  get_angles / get_dihedrals evaluate the index groups below on
+    #    the device; the NumPy forms (_angles, _dihedrals, _get_angles, _get_dihedrals: the reference's helpers, kept under
+    #    their names) are what the tests compare the device values with -------------------------------------------------
     def _residue_indices(self):
         """Per residue (first appearance order) the first index of N / CA / C / O / CB, -1 where absent."""
         info = self._atominfo
@@ -474,19 +479,42 @@ class MolearnAnalysis:
             out["CA-CB-C"] = self._angles(CA[:, valid], CB, C[:, valid])
         return out
 
+    def _dihedral_groups(self):
+        """Atom quadruples of the backbone dihedrals (analyser.py:491-516): Phi C(i-1)-N-CA-C, Psi N-CA-C-N(i+1),
+        Omega CA-C-N(i+1)-CA(i+1), and N-CA-C-CB where a CB exists."""
+        idx = self._residue_indices()
+        N, CA, C, CB = idx["N"], idx["CA"], idx["C"], idx["CB"]
+        g = {"Phi": np.stack([C[:-1], N[1:], CA[1:], C[1:]], axis=1),
+             "Psi": np.stack([N[:-1], CA[:-1], C[:-1], N[1:]], axis=1),
+             "Omega": np.stack([CA[:-1], C[:-1], N[1:], CA[1:]], axis=1)}
+        valid = CB >= 0
+        if valid.any():
+            g["Improper Torsion"] = np.stack([N[valid], CA[valid], C[valid], CB[valid]], axis=1)
+        return g
+
+    def _angle_groups(self):
+        """Atom triples of the backbone angles (analyser.py:535-564)."""
+        idx = self._residue_indices()
+        N, CA, C, O, CB = idx["N"], idx["CA"], idx["C"], idx["O"], idx["CB"]
+        g = {"N-CA-C": np.stack([N, CA, C], axis=1), "CA-C-N": np.stack([CA[:-1], C[:-1], N[1:]], axis=1),
+             "C-N-CA": np.stack([C[:-1], N[1:], CA[1:]], axis=1)}
+        if (O >= 0).all():
+            g["CA-C-O"] = np.stack([CA, C, O], axis=1)
+            g["O-C-N"] = np.stack([O[:-1], C[:-1], N[1:]], axis=1)
+        valid = CB >= 0
+        if valid.any():
+            g["N-CA-CB"] = np.stack([N[valid], CA[valid], CB[valid]], axis=1)
+            g["CA-CB-C"] = np.stack([CA[valid], CB[valid], C[valid]], axis=1)
+        return g
+
     def get_dihedrals(self, key):
-        ds, dec = self._structures(key)
-        out = dict(decoded_dihedrals=self._get_dihedrals(dec))
-        if ds is not None:
-            out["dataset_dihedrals"] = self._get_dihedrals(ds)
-        return out
+        """Backbone dihedrals of a dataset and of its decoded counterpart, ``{name: [F, n]}`` radians
+        (analyser.py:475-516), computed on the device."""
+        return self._internal(key, self._dihedral_groups(), "dihedrals", transpose=False)
 
     def get_angles(self, key):
-        ds, dec = self._structures(key)
-        out = dict(decoded_angles=self._get_angles(dec))
-        if ds is not None:
-            out["dataset_angles"] = self._get_angles(ds)
-        return out
+        """Backbone bond angles, ``{name: [F, n]}`` radians (analyser.py:518-566), computed on the device."""
+        return self._internal(key, self._angle_groups(), "angles", transpose=False)
 
     def _scan_geometry(self):
         if "_geometry_rows" not in self.__dict__ or self._geometry_rows_grid is not self._encoded.get("grid"):

@@ -116,3 +116,58 @@ class GeometryStats:
                 self.quad_t.data_ptr() if len(self.quads) else None, len(self.quads), out.data_ptr(),
                 torch.cuda.current_stream(x.device).cuda_stream))
         return out
+
+
+class InternalCoords:
+    """Device tables + launcher of ``mlp_internal_coords_eval``: named groups of atom pairs (distances), triples
+    (angles) and quadruples (dihedrals) evaluated for every structure of a batch on the GPU.
+
+    ``groups``: ``{name: int array [n, 2 | 3 | 4]}``.  ``__call__(x [B,N,3], scale)`` returns ``{name: [B, n]}``
+    float32 CUDA tensors (views of one output buffer; distances are multiplied by ``scale``)."""
+
+    def __init__(self, groups, device):
+        import numpy as np
+        self.device = torch.device(device)
+        self.slices = {}
+        parts = {2: [], 3: [], 4: []}
+        for name, idx in groups.items():
+            a = np.asarray(idx, dtype=np.int32).reshape(len(idx), -1)
+            if a.shape[1] not in parts:
+                raise ValueError(f"group {name}: expected index rows of 2, 3 or 4 atoms, got {a.shape}")
+            if a.size and a.min() < 0:
+                raise ValueError(f"group {name}: negative atom index")
+            parts[a.shape[1]].append((name, a))
+        self.counts = {}
+        self.tables = {}
+        off = 0
+        for k in (2, 3, 4):
+            rows = 0
+            for name, a in parts[k]:
+                self.slices[name] = (off + rows, off + rows + len(a))
+                rows += len(a)
+            self.counts[k] = rows
+            cat = np.concatenate([a for _, a in parts[k]]) if rows else np.zeros((0, k), np.int32)
+            self.tables[k] = torch.from_numpy(np.ascontiguousarray(cat)).to(self.device)
+            off += rows
+        self.n_all = off
+        self.max_index = max([int(t.max()) for t in self.tables.values() if t.numel()] + [-1])
+
+    def __call__(self, x, scale: float = 1.0):
+        _check_structures(x)
+        if x.device != self.device:
+            raise ValueError(f"x lives on {x.device}, the index tables on {self.device}")
+        if x.shape[1] <= self.max_index:
+            raise ValueError(f"structures have {x.shape[1]} atoms, the index lists address atom {self.max_index}")
+        B = x.shape[0]
+        out = torch.empty((B, self.n_all), dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            for lo in range(0, B, 32768):
+                xs, os_ = x[lo:lo + 32768], out[lo:lo + 32768]
+                _lib.check(L.mlp_internal_coords_eval(
+                    xs.data_ptr(), xs.shape[0], xs.stride(0), xs.stride(2), xs.stride(1), float(scale),
+                    self.tables[2].data_ptr() if self.counts[2] else None, self.counts[2],
+                    self.tables[3].data_ptr() if self.counts[3] else None, self.counts[3],
+                    self.tables[4].data_ptr() if self.counts[4] else None, self.counts[4],
+                    os_.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream))
+        return {name: out[:, a:b] for name, (a, b) in self.slices.items()}

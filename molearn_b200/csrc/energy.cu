@@ -1344,6 +1344,55 @@ geom_stats_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, flo
     }
 }
 
+// Internal coordinates of every structure: pair distances, bond angles and dihedral angles over index lists -
+// the device form of MolearnAnalysis.get_bondlengths / get_angles / get_dihedrals (analyser.py:418-566 with the
+// formulas of :791-861): only [B, n] scalars leave the GPU instead of the decoded [B, N, 3] structures.
+// angle(p0,p1,p2) = acos(b0^ . b1^), b0 = p0-p1, b1 = p2-p1; dihedral(p0,p1,p2,p3) = atan2((b1^ x v) . w, v . w) with
+// v, w the components of p0-p1 and p3-p2 orthogonal to b1 = p2-p1 (the standard formula; analyser.py:826 multiplies two
+// sums where it means the sum of a product).  fp64 arithmetic on the fp32 coordinates: a few thousand values per structure.
+__global__ void __launch_bounds__(128)
+internal_coords_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, float scale,
+                       const int2* __restrict__ pairs, int n_pairs, const int* __restrict__ triples, int n_triples,
+                       const int4* __restrict__ quads, int n_quads, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_all = n_pairs + n_triples + n_quads;
+    if (e >= n_all) return;
+    const float* xb = x + (long)b * sxb;
+    auto at = [&](int n, double (&p)[3]) { const float* q = xb + (long)n * sxn; p[0] = q[0]; p[1] = q[sxc]; p[2] = q[2 * sxc]; };
+    auto dotd = [](const double (&a)[3], const double (&c)[3]) { return a[0] * c[0] + a[1] * c[1] + a[2] * c[2]; };
+    double v;
+    if (e < n_pairs) {
+        const int2 pr = pairs[e];
+        double p0[3], p1[3];
+        at(pr.x, p0); at(pr.y, p1);
+        double d[3] = {p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]};
+        v = sqrt(dotd(d, d)) * (double)scale;
+    } else if (e < n_pairs + n_triples) {
+        const int* t = triples + 3 * (e - n_pairs);
+        double p0[3], p1[3], p2[3];
+        at(t[0], p0); at(t[1], p1); at(t[2], p2);
+        double b0[3] = {p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]}, b1[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+        double c = dotd(b0, b1) / (sqrt(dotd(b0, b0)) * sqrt(dotd(b1, b1)));
+        v = acos(fmin(1.0, fmax(-1.0, c)));
+        if (c != c) v = c;
+    } else {
+        const int4 qd = quads[e - n_pairs - n_triples];
+        double p0[3], p1[3], p2[3], p3[3];
+        at(qd.x, p0); at(qd.y, p1); at(qd.z, p2); at(qd.w, p3);
+        double b0[3] = {p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]}, b1[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+        double b2[3] = {p3[0] - p2[0], p3[1] - p2[1], p3[2] - p2[2]};
+        const double inv = 1.0 / sqrt(dotd(b1, b1));
+        b1[0] *= inv; b1[1] *= inv; b1[2] *= inv;
+        const double s0 = dotd(b0, b1), s2 = dotd(b2, b1);
+        double vv[3] = {b0[0] - s0 * b1[0], b0[1] - s0 * b1[1], b0[2] - s0 * b1[2]};
+        double ww[3] = {b2[0] - s2 * b1[0], b2[1] - s2 * b1[1], b2[2] - s2 * b1[2]};
+        double cr[3] = {b1[1] * vv[2] - b1[2] * vv[1], b1[2] * vv[0] - b1[0] * vv[2], b1[0] * vv[1] - b1[1] * vv[0]};
+        v = atan2(dotd(cr, ww), dotd(vv, ww));
+    }
+    out[(long)b * n_all + e] = (float)v;
+}
+
 // FP32 FMA-pipe probe (bench.py measures the pipe's live peak with it, next to the nominal 148 x 128 x 2 x f):
 // 8 independent chains of FFMA (packed = 0) or FFMA2 (packed = 1) per thread, 16 lane-FMAs per chain step.
 constexpr int PROBE_BLOCKS = 148 * 8, PROBE_THREADS = 256;
@@ -2066,6 +2115,24 @@ int mlp_rmsd_eval(const float* x, int64_t B, int64_t N, int64_t sxb, int64_t sxc
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { mlp_set_error(std::string("rmsd kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
+    return MLP_OK;
+}
+
+int mlp_internal_coords_eval(const float* x, int64_t B, int64_t sxb, int64_t sxc, int64_t sxn, float scale,
+                             const int32_t* pairs, int64_t n_pairs, const int32_t* triples, int64_t n_triples,
+                             const int32_t* quads, int64_t n_quads, float* out, void* stream_) {
+    const int64_t n_all = n_pairs + n_triples + n_quads;
+    if (B == 0 || n_all == 0) return MLP_OK;
+    if (!x || !out || B < 0 || B > 65535 || n_pairs < 0 || n_triples < 0 || n_quads < 0 || n_all > (1LL << 30) ||
+        (n_pairs > 0 && !pairs) || (n_triples > 0 && !triples) || (n_quads > 0 && !quads)) {
+        mlp_set_error("mlp_internal_coords_eval: bad argument (at most 65535 structures per call)");
+        return MLP_E_ARG;
+    }
+    internal_coords_kernel<<<dim3((unsigned)((n_all + 127) / 128), (unsigned)B), 128, 0, static_cast<cudaStream_t>(stream_)>>>(
+        x, sxb, sxc, sxn, scale, reinterpret_cast<const int2*>(pairs), (int)n_pairs, triples, (int)n_triples,
+        reinterpret_cast<const int4*>(quads), (int)n_quads, out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { mlp_set_error(std::string("internal-coordinates kernel launch: ") + cudaGetErrorString(err)); return MLP_E_CUDA; }
     return MLP_OK;
 }
 

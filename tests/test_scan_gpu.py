@@ -228,3 +228,38 @@ def test_fused_decoder_matches_plain_decode_gpu():
     finally:
         torch.backends.cudnn.allow_tf32 = old
     assert fused.fused_ok, "cuDNN fused conv+bias+relu was not available: the decoder ran the unfused fallback"
+
+
+def test_internal_coordinates_on_device_vs_numpy(analysis, murd_data):
+    """get_bondlengths / get_angles / get_dihedrals / get_inversions evaluate their index groups on the device
+    (mlp_internal_coords_eval; nothing of size [F, N, 3] is staged on the host).  Checked against the reference's NumPy
+    formulas (analyser.py:791-861, the dihedral in its standard form) applied to the same structures, for the MD frames
+    and for their decoded counterparts."""
+    ma = analysis
+    enc = ma.get_encoded("train")
+    with torch.no_grad():
+        dec = (ma._decode(enc.to(ma.device)) * ma.stdval + ma.meanval).double().cpu().numpy()
+    ds = murd_data.coords.astype(np.float64)
+    dih, ang, bl = ma.get_dihedrals("train"), ma.get_angles("train"), ma.get_bondlengths("train")
+    for which, x in (("dataset", ds), ("decoded", dec)):
+        want_d, want_a = ma._get_dihedrals(x), ma._get_angles(x)
+        assert set(dih[f"{which}_dihedrals"]) == set(want_d) == {"Phi", "Psi", "Omega", "Improper Torsion"}
+        for k, w in want_d.items():
+            got = dih[f"{which}_dihedrals"][k]
+            assert got.shape == w.shape == (16, len(w[0]))
+            d = np.abs(np.angle(np.exp(1j * (got - w))))                   # compare on the circle
+            assert d.max() < (2e-5 if which == "dataset" else 2e-3), (which, k, d.max())   # decoded: collapsed, ill-conditioned geometry in fp32
+        assert set(ang[f"{which}_angles"]) == set(want_a)
+        for k, w in want_a.items():
+            got = ang[f"{which}_angles"][k]
+            assert got.shape == w.shape and np.abs(got - w).max() < (2e-5 if which == "dataset" else 2e-3), (which, k)
+        from molearn_b200.analysis import backbone_indices
+        bonds, _ = backbone_indices(murd_data.get_atominfo())
+        for k, v in bonds.items():
+            w = np.array([np.linalg.norm(x[:, i, :] - x[:, j, :], axis=1) for i, j in v])
+            got = bl[f"{which}_bondlen"][k]
+            assert got.shape == w.shape and np.allclose(got, w, rtol=2e-5, atol=2e-5), (which, k)
+    assert abs(np.degrees(ang["dataset_angles"]["N-CA-C"]).mean() - 111) < 3
+    # a grid key has no dataset side
+    only = ma.get_angles("grid")
+    assert set(only) == {"decoded_angles"} and only["decoded_angles"]["N-CA-C"].shape == (36, 437)
