@@ -106,6 +106,10 @@ struct BTile {
     int cnt_off, pad;
 };
 
+struct NbBlockItem;
+constexpr int NB_BLK_LEVELS = 3;
+constexpr int NB_BLK_ROWS[NB_BLK_LEVELS] = {2, 4, 8};
+
 struct mlp_energy {
     int device = 0;
     uint32_t nb_mode = 0;
@@ -131,6 +135,19 @@ struct mlp_energy {
     float2* d_par = nullptr;       // [Npad] (R/2, sqrt(12 eps))
     int* d_red_off = nullptr;      // [n_nbt+1] per tile: range in d_red_list
     int* d_red_list = nullptr;     // entries pair*2 + side (0: the tile is the pair's I, 1: its J)
+    // block-item schedules of the pair term (nb_block_kernel): used when there is much more work than warp slots;
+    // level k walks blocks of NB_BLK_ROWS[k] rows x NB_BLK_C columns (bigger blocks need more work per slot)
+    struct BlockSchedule {
+        int rows = 0, items = 0, blocks = 0;   // items and partial-force blocks per conformation
+        NbBlockItem* d_items = nullptr;
+        int* d_red_off = nullptr;
+        int* d_red_list = nullptr;
+    } blk[NB_BLK_LEVELS];
+    int blk_acc_smem = 0;                // dynamic shared memory of a block-item CTA (j-force accumulators)
+    int blk_mode = -1;                   // -1: by work per warp slot, 0: never, R: always the level with R rows (MLP_NB_BLOCKS)
+    int2* d_pair_meta = nullptr;         // [nt(nt+1)/2] (mask index | -1, step bits) of tile pair (I, J >= I)
+    float* d_tpar = nullptr;             // [nt][3][128] charge, R/2, sqrt(12 eps)
+    float* d_tparw = nullptr;            // [nt][3][128] charge, a, b (product form of the repulsive mode)
     int last_launches = 0;
     int sm_count = 148;
     // side stream: the (latency-bound) bonded kernel runs next to the non-bonded pair kernel
@@ -1054,6 +1071,236 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     }
 }
 
+// ---- block-item variant: large batches x systems ------------------------------------------------------------
+// nb_kernel2 gives every 128 x 128 tile pair its own warp and its own pair of partial-force blocks: the finest
+// granularity (what a MurD-sized batch of 64 needs to fill 148 SMs evenly), at the price of 3 KB of scratch per tile
+// pair and conformation and of one prologue per 32 rotation steps.  When there is much more work than warp slots the
+// items below are used instead: one warp walks a BLOCK of tile pairs, rows I0..I0+R-1 times columns J0..J0+C-1,
+// row by row;
+//   * the row's 128 i-atoms and their force accumulators stay in registers across the row's C tiles and are written
+//     once per row;
+//   * the j-atom forces of a column are accumulated over the block's R rows in shared memory (fixed order, one warp:
+//     still reproducible) and written once per column - R + C partial blocks instead of 2 R C;
+//   * the next tile's j-atoms (coordinates with the caller's strides, packed per-tile parameters, exclusion masks) are
+//     fetched with cp.async into the other half of a double buffer while the current tile is evaluated.
+// Items are either rectangles strictly above the diagonal band (R <= NB_BLK_R, C <= NB_BLK_C) or single rows
+// (R = 1: the diagonal tile and the tiles up to the next rectangle).  Scratch per conformation drops from
+// 3 KB x tile pairs to about 1.5 KB x tile pairs x (1/R + 1/C).
+#define NB_BLK_R 8    // largest block height (NB_BLK_ROWS)
+#ifndef NB_BLK_C
+#define NB_BLK_C 4
+#endif
+static_assert(NB_BLK_R * NB_BLK_C <= 32, "the lanes of the warp preload the meta data of the item's tiles");
+struct NbBlockItem { int I0, R, J0, C, iblk, jblk, pad0, pad1; };   // iblk / jblk: first partial block of the rows / columns
+static_assert(sizeof(NbBlockItem) == 32, "record layout");
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <bool GRAD, bool FULL>
+__global__ void __launch_bounds__(32, 4 * NB2_MINB)
+nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N, int nt,
+                const float* __restrict__ tpar /* [nt][3][128]: charge, then the two per-atom LJ parameters */,
+                const NbBlockItem* __restrict__ items, const int2* __restrict__ pair_meta /* [nt(nt+1)/2]: mask index | -1, step bits */,
+                const uint32_t* __restrict__ masks, int n_items, int n_blocks, int B,
+                float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
+    __shared__ __align__(16) float s_j[2][6 * NB_T];          // double buffer: component c of the 128 j-atoms at [c*128 + jj]
+    __shared__ __align__(16) uint32_t s_m[2][NB_T * 4];       // uint16 [g][lane] pair masks of a masked tile, as words
+    extern __shared__ __align__(16) float s_acc[];            // [C][3][128] j-force accumulators of a rectangle (R > 1)
+    __shared__ int2 s_meta[32];                                // (mask index | -1, step bits) of the item's tiles
+    const int lane = threadIdx.x;
+    const long work = blockIdx.x;
+    const int q = (int)(work / B), b = (int)(work - (long)q * B);
+    if (weights && !e_part && weights[4 * b + 3] == 0.f) return;
+    const NbBlockItem it = items[q];
+    const float* xb = x + (long)b * sxb;
+    const int n_tile = it.R * it.C;
+    // tile t of the item = (row t / C, column t % C)
+    {
+        int2 m = make_int2(-1, 0);
+        if (lane < n_tile) {
+            const int I = it.I0 + lane / it.C, J = it.J0 + lane % it.C;
+            m = pair_meta[I * nt - (I * (I - 1)) / 2 + (J - I)];
+        }
+        s_meta[lane] = m;
+        __syncwarp();
+    }
+    auto issue = [&](int t, int buf) {
+        const int J = it.J0 + t % it.C;
+        const int j0 = J * NB_T;
+        float* dst = s_j[buf];
+#pragma unroll
+        for (int k = 0; k < NB_T / 32; ++k) {
+            const int jj = lane + 32 * k, n = j0 + jj;
+            if (n < N) {
+                const float* p = xb + (long)n * sxn;
+                cp_async4(dst + jj, p); cp_async4(dst + NB_T + jj, p + sxc); cp_async4(dst + 2 * NB_T + jj, p + 2 * sxc);
+            } else {   // padding of the last tile: parked far away (zero charge / LJ parameters in tpar)
+                dst[jj] = 1.0e6f + 100.f * (float)(n - N); dst[NB_T + jj] = -1.0e6f; dst[2 * NB_T + jj] = 1.0e6f;
+            }
+        }
+        const float* src = tpar + (long)J * (3 * NB_T);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cp_async16(dst + 3 * NB_T + 4 * (lane + 32 * k), src + 4 * (lane + 32 * k));
+        const int mi = s_meta[t].x;
+        if (mi >= 0) {
+            const uint32_t* ms = masks + (long)mi * (NB_T * 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cp_async16(s_m[buf] + 4 * (lane + 32 * k), ms + 4 * (lane + 32 * k));
+        }
+        cp_async_commit();
+    };
+    issue(0, 0);
+    if (n_tile > 1) issue(1, 1); else cp_async_commit();
+
+    float2 Sl = dup(0.f), Sc = dup(0.f);
+    ival xi[NB_NI][4], hRi[NB_NI], sei[NB_NI];
+    fval Fi[NB_NI][3];
+    const int src_lane = (lane + 1) & 31;
+    int t = 0;
+    for (int r = 0; r < it.R; ++r) {
+        const int I = it.I0 + r, i0 = I * NB_T;
+        {
+            const float4* tp = reinterpret_cast<const float4*>(tpar + (long)I * (3 * NB_T));
+            const float4 q4 = tp[lane], h4 = tp[32 + lane], s4 = tp[64 + lane];
+            const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, hv[4] = {h4.x, h4.y, h4.z, h4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int a = 0; a < NB_NI; ++a) {
+                const int n = i0 + 4 * lane + a;
+                float vx = 1.0e6f + 100.f * (float)(n - N), vy = -1.0e6f, vz = 1.0e6f;
+                if (n < N) { const float* p = xb + (long)n * sxn; vx = p[0]; vy = p[sxc]; vz = p[2 * sxc]; }
+                xi[a][0] = imake(vx); xi[a][1] = imake(vy); xi[a][2] = imake(vz); xi[a][3] = imake(qv[a]);
+                hRi[a] = imake(hv[a]); sei[a] = imake(sv[a]);
+                Fi[a][0] = Fi[a][1] = Fi[a][2] = fzero();
+            }
+        }
+        for (int c = 0; c < it.C; ++c, ++t) {
+            const int buf = t & 1;
+            if (t + 1 < n_tile) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncwarp();
+            const int J = it.J0 + c;
+            const int2 meta = s_meta[t];
+            const uint32_t sbits = meta.x >= 0 ? (uint32_t)meta.y : 0u;   // bit rs: rotation step rs touches an excluded pair
+            const int n_steps = (J == I) ? 17 : 32;            // diagonal tile: block (L,g) mirrors (g,L)
+            const float4(*sj)[32] = reinterpret_cast<const float4(*)[32]>(s_j[buf]);
+            const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m[buf]);
+            float2 Fj[2][3];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) Fj[pp][0] = Fj[pp][1] = Fj[pp][2] = dup(0.f);
+            auto fix_tile = [&](const float4 (&cj)[6], uint32_t m16) {
+                float4 ui[NB_NI], uj[4];
+                float2 upi[NB_NI], upj[4];
+                float3 dFi[NB_NI], dFj[4];
+                float dSl = 0.f, dSc = 0.f;
+#pragma unroll
+                for (int a = 0; a < NB_NI; ++a) {
+                    ui[a] = make_float4(ilo(xi[a][0]), ilo(xi[a][1]), ilo(xi[a][2]), ilo(xi[a][3]));
+                    upi[a] = make_float2(ilo(hRi[a]), ilo(sei[a]));
+                    dFi[a] = make_float3(0.f, 0.f, 0.f);
+                }
+                const float* cf = reinterpret_cast<const float*>(cj);
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                    uj[bb] = make_float4(cf[0 * 4 + bb], cf[1 * 4 + bb], cf[2 * 4 + bb], cf[3 * 4 + bb]);
+                    upj[bb] = make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
+                    dFj[bb] = make_float3(0.f, 0.f, 0.f);
+                }
+                nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+#pragma unroll
+                for (int a = 0; a < NB_NI; ++a) { faddlo(Fi[a][0], dFi[a].x); faddlo(Fi[a][1], dFi[a].y); faddlo(Fi[a][2], dFi[a].z); }
+                Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
+                Fj[0][0].y += dFj[1].x; Fj[0][1].y += dFj[1].y; Fj[0][2].y += dFj[1].z;
+                Fj[1][0].x += dFj[2].x; Fj[1][1].x += dFj[2].y; Fj[1][2].x += dFj[2].z;
+                Fj[1][0].y += dFj[3].x; Fj[1][1].y += dFj[3].y; Fj[1][2].y += dFj[3].z;
+                Sl.x += dSl; Sc.x += dSc;
+            };
+            auto rotate = [&]() {
+                if (GRAD) {
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            Fj[pp][cc].x = __shfl_sync(0xffffffffu, Fj[pp][cc].x, src_lane);
+                            Fj[pp][cc].y = __shfl_sync(0xffffffffu, Fj[pp][cc].y, src_lane);
+                        }
+                }
+            };
+            int rs = 0;
+#pragma unroll 1
+            for (; rs < n_steps; ++rs) {
+                const int g = (lane + rs) & 31;
+                float4 cj[6];
+#pragma unroll
+                for (int cc = 0; cc < 6; ++cc) cj[cc] = sj[cc][g];
+                const bool mstep = (sbits >> rs) & 1u;
+                const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
+                const bool close = mstep ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
+                                         : nb_micro2<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+                if (close) fix_tile(cj, m16);
+                rotate();
+                if (NB_DENSE_MODE && rs == 0 && __popc(__ballot_sync(0xffffffffu, close)) >= 16) { ++rs; break; }
+            }
+#pragma unroll 1
+            for (; rs < n_steps; ++rs) {       // collapsed structures: every pair exactly, no fast path
+                const int g = (lane + rs) & 31;
+                float4 cj[6];
+#pragma unroll
+                for (int cc = 0; cc < 6; ++cc) cj[cc] = sj[cc][g];
+                const bool mstep = (sbits >> rs) & 1u;
+                const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
+                if (mstep) nb_micro2_exact<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+                else nb_micro2_exact<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+                rotate();
+            }
+            if (GRAD) {
+                const int gl = (lane + n_steps) & 31;          // after n_steps rotations the lane holds the forces of this group
+                if (it.R == 1) {
+                    float* out = fpart + ((long)b * n_blocks + it.jblk + c) * (3 * NB_T);
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+                        reinterpret_cast<float4*>(out + cc * NB_T)[gl] = make_float4(Fj[0][cc].x, Fj[0][cc].y, Fj[1][cc].x, Fj[1][cc].y);
+                } else {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        float4* a4 = reinterpret_cast<float4*>(s_acc + (c * 3 + cc) * NB_T) + gl;
+                        float4 v = make_float4(Fj[0][cc].x, Fj[0][cc].y, Fj[1][cc].x, Fj[1][cc].y);
+                        if (r > 0) { const float4 o = *a4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        *a4 = v;
+                    }
+                }
+            }
+            __syncwarp();                                       // every lane is done with this half of the double buffer
+            if (t + 2 < n_tile) issue(t + 2, buf); else cp_async_commit();
+        }
+        if (GRAD) {
+            float* out = fpart + ((long)b * n_blocks + it.iblk + r) * (3 * NB_T);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+                reinterpret_cast<float4*>(out + cc * NB_T)[lane] =
+                    make_float4(-fsum(Fi[0][cc]), -fsum(Fi[1][cc]), -fsum(Fi[2][cc]), -fsum(Fi[3][cc]));
+        }
+    }
+    if (GRAD && it.R > 1) {
+        __syncwarp();
+        for (int c = 0; c < it.C; ++c) {
+            float* out = fpart + ((long)b * n_blocks + it.jblk + c) * (3 * NB_T);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+                reinterpret_cast<float4*>(out + cc * NB_T)[lane] = reinterpret_cast<const float4*>(s_acc + (c * 3 + cc) * NB_T)[lane];
+        }
+    }
+    if (e_part) {
+        double e = (double)warp_sum(Sl.x + Sl.y) * (1.0 / 12.0) + (double)warp_sum(Sc.x + Sc.y);
+        if (lane == 0) e_part[(long)b * n_items + q] = e;
+    }
+}
+
 // grad[b, n] (+)= w_nb[b] * (sum of the partial forces of every tile pair in n's tile row / column),
 // summed in list order: reproducible.
 #ifndef RED_PARTS_N
@@ -1062,7 +1309,8 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
 constexpr int RED_PARTS = RED_PARTS_N;     // warps of a reduction CTA: each sums one contiguous quarter of an atom's block list
 __global__ void __launch_bounds__(32 * RED_PARTS)
 nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_off, const int* __restrict__ red_list,
-                 int n_pairs, int N, float* __restrict__ grad, long sgb, long sgc, long sgn,
+                 int n_pairs /* energy partials per conformation */, int n_blocks /* partial-force blocks per conformation */,
+                 int N, float* __restrict__ grad, long sgb, long sgc, long sgn,
                  const float* __restrict__ weights, int accumulate, int skip_zero_weight,
                  const float* __restrict__ e_bonded, int n_tiles, const double* __restrict__ e_nb,
                  float* __restrict__ energies /* null: no energy output */, uint32_t term_mask) {
@@ -1106,7 +1354,7 @@ nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_of
         return;
     }
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    const float* base = fpart + (long)b * n_pairs * (6 * NB_T) + l;
+    const float* base = fpart + (long)b * n_blocks * (3 * NB_T) + l;
     const int k0 = red_off[T], k1 = red_off[T + 1];
     const int per = (k1 - k0 + RED_PARTS - 1) / RED_PARTS;
     const int ka = min(k1, k0 + part * per), kb = min(k1, ka + per);
@@ -1116,7 +1364,7 @@ nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_of
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = red_list[k + u];
-            const float* p = base + (long)(e >> 1) * (6 * NB_T) + (e & 1) * (3 * NB_T);
+            const float* p = base + (long)e * (3 * NB_T);       // entry = block index (nb_kernel2: pair*2 + side)
             vx[u] = p[0]; vy[u] = p[NB_T]; vz[u] = p[2 * NB_T];
         }
 #pragma unroll
@@ -1124,7 +1372,7 @@ nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_of
     }
     for (; k < kb; ++k) {
         const int e = red_list[k];
-        const float* p = base + (long)(e >> 1) * (6 * NB_T) + (e & 1) * (3 * NB_T);
+        const float* p = base + (long)e * (3 * NB_T);
         sx += p[0]; sy += p[NB_T]; sz += p[2 * NB_T];
     }
     s_part[part][0][lane] = sx; s_part[part][1][lane] = sy; s_part[part][2][lane] = sz;
@@ -1726,6 +1974,7 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     for (int t = 0; t < nt; ++t) ex[{t, t}];  // diagonal tiles are always masked (j > i)
     std::vector<int4> band, clean, diag;
     std::vector<uint32_t> masks, stepbits;
+    std::map<std::pair<int, int>, int> mask_of;   // tile pair -> mask index
     for (auto& kv : ex) {
         const int I = kv.first.first, J = kv.first.second;
         // uint16 [g][lane]: bit 4a+b <-> pair (i = 4*lane+a, j = 4g+b) allowed
@@ -1747,6 +1996,7 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
             for (auto& pr : kv.second) clear(pr.first - I * NB_T, pr.second - J * NB_T);
         }
         const int mi = (int)(masks.size() / (NB_T * 4));
+        mask_of[{I, J}] = mi;
         std::vector<uint32_t> m((size_t)NB_T * 4);
         std::memcpy(m.data(), m16.data(), m.size() * sizeof(uint32_t));
         masks.insert(masks.end(), m.begin(), m.end());
@@ -1783,7 +2033,56 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
         red_list.insert(red_list.end(), lists[t].begin(), lists[t].end());
         red_off[t + 1] = (int)red_list.size();
     }
+    // ---- block-item schedule (nb_block_kernel) ----
+    std::vector<float> tpar((size_t)nt * 3 * NB_T), tparw((size_t)nt * 3 * NB_T);
+    for (int n = 0; n < E->Npad; ++n) {
+        const size_t o = (size_t)(n / NB_T) * 3 * NB_T + n % NB_T;
+        tpar[o] = q[n]; tpar[o + NB_T] = par[n].x; tpar[o + 2 * NB_T] = par[n].y;
+        tparw[o] = q[n]; tparw[o + NB_T] = parw[n].x; tparw[o + 2 * NB_T] = parw[n].y;
+    }
+    std::vector<int2> pair_meta((size_t)nt * (nt + 1) / 2, make_int2(-1, 0));
+    auto pid = [&](int I, int J) { return (size_t)I * nt - (size_t)I * (I - 1) / 2 + (J - I); };
+    for (auto& kv : mask_of) pair_meta[pid(kv.first.first, kv.first.second)] = make_int2(kv.second, (int)stepbits[kv.second]);
+    E->blk_acc_smem = NB_BLK_C * 3 * NB_T * (int)sizeof(float);
     int rc;
+    for (int lv = 0; lv < NB_BLK_LEVELS; ++lv) {
+        const int RB = NB_BLK_ROWS[lv];
+        std::vector<NbBlockItem> bitems;
+        for (int I0 = 0; I0 < nt; I0 += RB) {
+            const int R = std::min(RB, nt - I0);
+            for (int I = I0; I < I0 + R; ++I)                          // the diagonal band of the block row: single rows
+                bitems.push_back(NbBlockItem{I, 1, I, I0 + R - I, 0, 0, 0, 0});
+            for (int J0 = I0 + R; J0 < nt; J0 += NB_BLK_C)            // rectangles strictly above it
+                bitems.push_back(NbBlockItem{I0, R, J0, std::min(NB_BLK_C, nt - J0), 0, 0, 0, 0});
+        }
+        auto cost = [&](const NbBlockItem& b) {
+            long c = 0;
+            for (int r = 0; r < b.R; ++r) for (int k = 0; k < b.C; ++k) c += (b.I0 + r == b.J0 + k) ? 17 : 32;
+            return c;
+        };
+        std::stable_sort(bitems.begin(), bitems.end(), [&](const NbBlockItem& a, const NbBlockItem& b) { return cost(a) > cost(b); });
+        std::vector<std::vector<int>> blists(nt);
+        int nblk = 0;
+        for (NbBlockItem& b : bitems) {
+            b.iblk = nblk; nblk += b.R;
+            b.jblk = nblk; nblk += b.C;
+            for (int r = 0; r < b.R; ++r) blists[b.I0 + r].push_back(b.iblk + r);
+            for (int k = 0; k < b.C; ++k) blists[b.J0 + k].push_back(b.jblk + k);
+        }
+        std::vector<int> bred_off(nt + 1, 0), bred_list;
+        for (int t = 0; t < nt; ++t) {
+            bred_list.insert(bred_list.end(), blists[t].begin(), blists[t].end());
+            bred_off[t + 1] = (int)bred_list.size();
+        }
+        auto& S = E->blk[lv];
+        S.rows = RB; S.items = (int)bitems.size(); S.blocks = nblk;
+        if ((rc = upload(E, &S.d_items, bitems))) return rc;
+        if ((rc = upload(E, &S.d_red_off, bred_off))) return rc;
+        if ((rc = upload(E, &S.d_red_list, bred_list))) return rc;
+    }
+    if ((rc = upload(E, &E->d_pair_meta, pair_meta))) return rc;
+    if ((rc = upload(E, &E->d_tpar, tpar))) return rc;
+    if ((rc = upload(E, &E->d_tparw, tparw))) return rc;
     if ((rc = upload(E, &E->d_pairs, pairs))) return rc;
     if ((rc = upload(E, &E->d_masks, masks))) return rc;
     if ((rc = upload(E, &E->d_stepbits, stepbits))) return rc;
@@ -1797,14 +2096,36 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
 
 struct Workspace { size_t e_bonded, e_nb, fpart, total; };
 
+// The pair term runs as block items (nb_block_kernel) when every resident warp slot gets at least NB_BLK_MIN_ITEMS
+// items of the block size; below that the one-tile-pair items of nb_kernel2 balance the SMs better.  A pure function of the
+// handle and the batch size: mlp_energy_workspace_bytes and mlp_energy_eval agree on it.
+#ifndef NB_BLK_MIN_ITEMS
+#define NB_BLK_MIN_ITEMS 8
+#endif
+int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pair (nb_kernel2)
+    if (!e->packed || e->blk_mode == 0) return -1;
+    if (e->blk_mode > 0) {
+        for (int lv = 0; lv < NB_BLK_LEVELS; ++lv) if (NB_BLK_ROWS[lv] == e->blk_mode) return lv;
+        return NB_BLK_LEVELS - 1;
+    }
+    const double per_slot = (double)e->n_nbt * (e->n_nbt + 1) / 2 * (double)B / ((double)e->sm_count * 4 * NB2_MINB);
+    int best = -1;
+    for (int lv = 0; lv < NB_BLK_LEVELS; ++lv)        // an item of R x C tile pairs wants >= NB_BLK_MIN_ITEMS items per slot
+        if (per_slot >= (double)NB_BLK_MIN_ITEMS * NB_BLK_ROWS[lv] * NB_BLK_C) best = lv;
+    return best;
+}
+// partial-force blocks (3 x 128 floats) and energy partials per conformation under the schedule in use
+int nb_blocks(const mlp_energy* e, int64_t B) { const int lv = block_level(e, B); return lv >= 0 ? e->blk[lv].blocks : 2 * e->n_pairs; }
+int nb_eparts(const mlp_energy* e, int64_t B) { const int lv = block_level(e, B); return lv >= 0 ? e->blk[lv].items : e->n_pairs; }
+
 Workspace layout(const mlp_energy* e, int64_t B, uint32_t term_mask, bool grad) {
     Workspace w{};
     size_t off = 0;
     w.e_bonded = off; off += align256((size_t)B * std::max(e->n_tiles, 1) * 3 * sizeof(float));
     w.e_nb = off;
-    if (term_mask & MLP_TERM_NB) off += align256((size_t)B * e->n_pairs * sizeof(double));
+    if (term_mask & MLP_TERM_NB) off += align256((size_t)B * nb_eparts(e, B) * sizeof(double));
     w.fpart = off;
-    if ((term_mask & MLP_TERM_NB) && grad) off += align256((size_t)B * e->n_pairs * 6 * NB_T * sizeof(float));
+    if ((term_mask & MLP_TERM_NB) && grad) off += align256((size_t)B * nb_blocks(e, B) * 3 * NB_T * sizeof(float));
     w.total = off + 256;
     return w;
 }
@@ -1874,6 +2195,7 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
     if (rc == MLP_OK) {
         if (const char* env = std::getenv("MLP_NO_OVERLAP")) E->overlap = std::atoi(env) == 0;
         if (const char* env = std::getenv("MLP_NB_FIRST")) E->nb_first = std::atoi(env) != 0;
+        if (const char* env = std::getenv("MLP_NB_BLOCKS")) E->blk_mode = std::max(0, std::atoi(env));   // 0: never, 2/4/8: always that block height
         if (const char* env = std::getenv("MLP_NB_PACKED")) E->packed = std::atoi(env) != 0;
         if (cudaStreamCreateWithFlags(&E->side, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -2059,13 +2381,22 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         double* ep = energies ? e_nb : nullptr;
 #define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
 #define NB_LAUNCH2(G, F) nb_kernel2<G, F><<<(unsigned)items, 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, (int)B, fpart, weights, ep)
-        if (e->packed) {
+        const int lv = block_level(e, B);
+        const bool blocks_on = lv >= 0;
+        const mlp_energy::BlockSchedule& S = e->blk[blocks_on ? lv : 0];
+#define NB_LAUNCHB(G, F) nb_block_kernel<G, F><<<(unsigned)((long)B * S.items), 32, e->blk_acc_smem, stream>>>(x, sxb, sxc, sxn, N, e->n_nbt, \
+            (NB_WFORM && !F) ? e->d_tparw : e->d_tpar, S.d_items, e->d_pair_meta, e->d_masks, S.items, S.blocks, (int)B, fpart, weights, ep)
+        if (blocks_on) {
+            if (grad) { if (full) NB_LAUNCHB(true, true); else NB_LAUNCHB(true, false); }
+            else { if (full) NB_LAUNCHB(false, true); else NB_LAUNCHB(false, false); }
+        } else if (e->packed) {
             if (grad) { if (full) NB_LAUNCH2(true, true); else NB_LAUNCH2(true, false); }
             else { if (full) NB_LAUNCH2(false, true); else NB_LAUNCH2(false, false); }
         } else {
             if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
             else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
         }
+#undef NB_LAUNCHB
 #undef NB_LAUNCH2
 #undef NB_LAUNCH
         LAUNCH_CHECK("the non-bonded pair kernel");
@@ -2078,7 +2409,8 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient (and sums its energy partials)
         if (grad) {
             prof_begin(3);
-            nb_reduce_kernel<<<dim3(e->n_nbt * (NB_T / 32), (unsigned)B), 32 * RED_PARTS, 0, stream>>>(fpart, e->d_red_off, e->d_red_list, e->n_pairs, N,
+            nb_reduce_kernel<<<dim3(e->n_nbt * (NB_T / 32), (unsigned)B), 32 * RED_PARTS, 0, stream>>>(fpart,
+                blocks_on ? S.d_red_off : e->d_red_off, blocks_on ? S.d_red_list : e->d_red_list, nb_eparts(e, B), nb_blocks(e, B), N,
                 grad, sgb, sgc, sgn, weights, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0,
                 e_bonded, e->n_tiles, e_nb, energies, term_mask);
             LAUNCH_CHECK("nb_reduce_kernel");
@@ -2088,7 +2420,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         }
     }
     if (energies && !energies_done) {
-        finalize_kernel<<<(unsigned)B, 128, 0, stream>>>(e_bonded, e->n_tiles, e_nb, e->n_pairs, energies, term_mask);
+        finalize_kernel<<<(unsigned)B, 128, 0, stream>>>(e_bonded, e->n_tiles, e_nb, nb_eparts(e, B), energies, term_mask);
         LAUNCH_CHECK("finalize_kernel");
         ++launches;
     }

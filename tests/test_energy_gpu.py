@@ -401,7 +401,8 @@ def test_conformation_extent_limit_is_reported(dev, energy_objs, golden_energy):
         _lib.check(rc)
 
 
-@pytest.mark.parametrize("knob", ["MLP_NB_PACKED=0", "MLP_NO_OVERLAP=1", "MLP_BONDED_TILE=64", "MLP_BONDED_TILE=40"])
+@pytest.mark.parametrize("knob", ["MLP_NB_PACKED=0", "MLP_NO_OVERLAP=1", "MLP_BONDED_TILE=64", "MLP_BONDED_TILE=40", "MLP_NB_BLOCKS=8", "MLP_NB_BLOCKS=2",
+                                  "MLP_NB_FIRST=1"])
 def test_alternative_code_paths_agree(knob, dev, golden_topo, golden_energy, monkeypatch):
     """The library's run-time switches (read when a handle is created) select other code paths of the same maths: the
     scalar pair kernel, no side-stream overlap, smaller bonded tiles (other work-item matchings and halos).  Each must
@@ -537,3 +538,44 @@ def test_51k_atoms_coincident_atoms_semantics(dev, system_51k):
         xs[0, j] = xs[0, i]
     got, want, _, _ = _check_51k(tpe, topo, xs, dev, [TOL, TOL, 1e-4, TOL], "coincident")
     assert np.isfinite(got[0]) and np.isnan(got[1]) and np.isfinite(got[2]) and np.isfinite(got[3])
+
+
+def test_block_item_schedule_matches_tile_pair_schedule(dev, monkeypatch):
+    """The two schedules of the pair term - one warp per tile pair (nb_kernel2) and one warp per block of tile pairs
+    (nb_block_kernel: rows kept in registers, column forces accumulated in shared memory, cp.async double buffering) -
+    on the 10 715-atom system: MD-like, noisy and collapsed conformations, both NB modes; against each other and
+    against the fp64 oracle.  The block schedule needs less scratch."""
+    from molearn_b200 import TorchProteinEnergy, _lib
+    from molearn_b200.data import tile_system
+    g = load_golden_murd_bbcb()
+    tinfo, x = tile_system(g[0], g[1], 5, batch=3, noise=0.3, seed=6)
+    x[2] = (x[2] - x[2].mean(0)) * 0.2 + np.random.default_rng(4).normal(scale=0.2, size=x[2].shape)      # collapsed
+    xd = torch.from_numpy(x.astype(np.float32)).to(dev).permute(0, 2, 1)
+    for NB in ("repulsive", "full"):
+        res, ws = {}, {}
+        for mode in ("0", "4", "8"):
+            monkeypatch.setenv("MLP_NB_BLOCKS", mode)
+            tpe = TorchProteinEnergy(None, tinfo, device=dev, NB=NB)
+            res[mode] = tpe.energy_and_gradient(xd)
+            ws[mode] = _lib.lib().mlp_energy_workspace_bytes(tpe._dev()._h, 1, _lib.TERM_ALL, 1)
+            topo = tpe.topology.as_dict()
+        (e0, g0), (e1, g1) = res["0"], res["8"]
+        for other in ("4", "8"):
+            assert torch.allclose(e0, res[other][0], rtol=2e-6), (NB, other, e0, res[other][0])
+            assert float((g0 - res[other][1]).norm() / g0.norm()) < 2e-6
+        assert ws["8"] < 0.3 * ws["0"] and ws["4"] < 0.4 * ws["0"], ws
+        for qi in (0, 2):
+            we, wg = eo.energy_all(x[qi].astype(np.float32), topo, full=NB == "full")
+            got = e1[qi].double().cpu().numpy()
+            assert abs(got[3] - we[3]) < TOL * abs(we[3]), (NB, qi, got[3], we[3])
+            assert rel(g1[qi].permute(1, 0).double().cpu().numpy(), wg.sum(0)) < TOL
+    # energy-only and weighted-backward paths of the block schedule
+    monkeypatch.setenv("MLP_NB_BLOCKS", "2")
+    tpe = TorchProteinEnergy(None, tinfo, device=dev)
+    xr = xd.detach().clone().requires_grad_(True)
+    e = tpe.energy_per_conformation(xr)
+    (e * torch.tensor([[1.0, 0.5, 2.0, -1.0], [0.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 3.0]], device=dev)).sum().backward()
+    with torch.no_grad():
+        e_only = tpe.energy_per_conformation(xd)
+    assert torch.equal(e.detach(), e_only)
+    assert (xr.grad[1] == 0).all() and torch.isfinite(xr.grad).all()

@@ -47,9 +47,26 @@ def run(tpe, x, reps, key):
 
 
 tpe = TorchProteinEnergy(None, info, device=dev)
-run(tpe, make_batch(frames, 0).to(dev), 50, "murd64")
-if "--big" in sys.argv or os.environ.get("NB_TIME_BIG", "1") == "1":
-    tinfo, x = tile_system(info, frames, 5, batch=32, noise=0.05, seed=1234)
-    tpe2 = TorchProteinEnergy(None, tinfo, device=dev)
-    run(tpe2, torch.from_numpy(x).to(dev), 5, "n10k32")
+cases = os.environ.get("NB_TIME_CASES", "murd64,n10k32" if os.environ.get("NB_TIME_BIG", "1") == "1" else "murd64").split(",")
+for case in cases:
+    if case.startswith("murd"):
+        Bc = int(case[4:])
+        xb = make_batch(frames, 0, min(Bc, 64)).to(dev)
+        if Bc > 64:
+            xb = xb.repeat(Bc // 64, 1, 1) + 0.01 * torch.randn(Bc, xb.shape[1], 3, device=dev)
+        run(tpe, xb, 50 if Bc <= 256 else 5, case)
+    elif case.startswith("n10k"):
+        Bc = int(case[4:])
+        tinfo, x = tile_system(info, frames, 5, batch=Bc, noise=0.05, seed=1234)
+        tpe2 = TorchProteinEnergy(None, tinfo, device=dev)
+        run(tpe2, torch.from_numpy(x).to(dev), 5, case)
+        out[case + "_ws_mb"] = _lib.lib().mlp_energy_workspace_bytes(tpe2._dev()._h, Bc, _lib.TERM_ALL, 1) / 2 ** 20
+        del tpe2
+    elif case.startswith("n51k"):
+        Bc = int(case[4:])
+        tinfo, x = tile_system(info, frames, 24, batch=Bc, noise=0.05, seed=1234)
+        tpe2 = TorchProteinEnergy(None, tinfo, device=dev)
+        run(tpe2, torch.from_numpy(x).to(dev), 3, case)
+        out[case + "_ws_mb"] = _lib.lib().mlp_energy_workspace_bytes(tpe2._dev()._h, Bc, _lib.TERM_ALL, 1) / 2 ** 20
+        del tpe2
 print(json.dumps({k: (round(v, 5) if isinstance(v, float) else v) for k, v in out.items()}))
