@@ -11,8 +11,8 @@
  * (openmm_thread.py:290-321).  Each declaration cites the reference code it replaces.
  *
  * Conventions
- *   - return value 0 = success, negative = error (MLP_E_*); the message of the last error of
- *     the calling thread is returned by mlp_last_error().
+ *   - return value >= 0 = success (0 unless stated otherwise), negative = error (MLP_E_*); the message of
+ *     the last error of the calling thread is returned by mlp_last_error().
  *   - "dev" pointers are device memory of the device the handle was created on; everything
  *     else is host memory.
  *   - no entry point allocates device memory, synchronises the device or copies to the host
@@ -161,6 +161,7 @@ int mlp_energy_info(const mlp_energy* e, int64_t info[8]);
  *   workspace  dev, >= mlp_energy_workspace_bytes(e,B,term_mask,grad!=NULL) bytes, 16-byte aligned
  *   stream     cudaStream_t
  * Non-finite coordinates are not an error: they propagate into that conformation's outputs.
+ * Returns the number of kernels it queued (>= 0) or a negative MLP_E_* code.
  *
  * Concurrency: work is ordered on `stream`; when both bonded and non-bonded terms are requested the bonded
  * kernel runs on a private stream of the handle that forks from and joins back into `stream` (so the call is

@@ -2426,7 +2426,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     }
 #undef LAUNCH_CHECK
     e->last_launches = launches;
-    return MLP_OK;
+    return launches;       // >= 0: success, the number of kernels queued (also mlp_energy_last_launches)
 }
 
 int mlp_rmsd_eval(const float* x, int64_t B, int64_t N, int64_t sxb, int64_t sxc, int64_t sxn, float scale, float shift,

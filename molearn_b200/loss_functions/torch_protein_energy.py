@@ -50,11 +50,14 @@ class _DeviceEnergy:
     def _workspace(self, nbytes, device):
         """Scratch buffer of the call.  The last one is kept and handed out again: allocations made on one stream
         are reused by later calls on the same stream only (the caching allocator's rule, applied by hand)."""
-        stream = torch.cuda.current_stream(device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture: the scratch must come from the graph's own memory pool and stay with the graph
+            return torch.empty(nbytes, dtype=torch.uint8, device=device), stream
         ws = self._ws
-        if ws is None or ws[0].numel() < nbytes or ws[1] != stream.cuda_stream:
-            ws = self._ws = (torch.empty(nbytes, dtype=torch.uint8, device=device), stream.cuda_stream)
-        return ws[0], stream.cuda_stream
+        if ws is None or ws[0].numel() < nbytes or ws[1] != stream:
+            ws = self._ws = (torch.empty(nbytes, dtype=torch.uint8, device=device), stream)
+        return ws[0], stream
 
     def eval(self, x, energies, grad, weights, term_mask, accumulate=False):
         """x: [B,3,N] logical fp32 CUDA tensor (any strides). energies [B,4] or None; grad like x or None."""
@@ -78,14 +81,16 @@ class _DeviceEnergy:
         ws, stream = self._workspace(nbytes, x.device)
         gs = grad.stride() if grad is not None else (0, 0, 0)
         xs = x.stride()
-        _lib.check(L.mlp_energy_eval(
+        rc = L.mlp_energy_eval(
             self._h, x.data_ptr(), B, xs[0], xs[1], xs[2],
             energies.data_ptr() if energies is not None else None,
             grad.data_ptr() if grad is not None else None, gs[0], gs[1], gs[2],
             weights.data_ptr() if weights is not None else None,
             term_mask, _lib.EVAL_ACCUMULATE_GRAD if accumulate else 0,
-            ws.data_ptr(), nbytes, stream))
-        self.launches += L.mlp_energy_last_launches(self._h)
+            ws.data_ptr(), nbytes, stream)
+        if rc < 0:
+            _lib.check(rc)
+        self.launches += rc                                             # kernels queued by this call
 
     def profile(self, enable: bool):
         _lib.check(_lib.lib().mlp_energy_profile(self._h, int(enable)))

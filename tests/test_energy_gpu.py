@@ -579,3 +579,26 @@ def test_block_item_schedule_matches_tile_pair_schedule(dev, monkeypatch):
         e_only = tpe.energy_per_conformation(xd)
     assert torch.equal(e.detach(), e_only)
     assert (xr.grad[1] == 0).all() and torch.isfinite(xr.grad).all()
+
+
+def test_graphed_step_equals_eager(dev, energy_objs, golden_energy):
+    """GraphedEnergyStep: H2D + energy + backward + D2H captured into one CUDA graph per pinned buffer (through the
+    autograd Function), replayed over two streams - bit-identical to the eager call, also after the buffers change."""
+    from molearn_b200.loss_functions import GraphedEnergyStep
+    tpe = energy_objs("bbcb")
+    x0 = torch.from_numpy(golden_energy("bbcb")["x"])                  # [14,N,3]
+    bufs = [x0.clone().pin_memory(), (x0 + 0.05).pin_memory(), x0.flip(0).contiguous().pin_memory()]
+    step = GraphedEnergyStep(tpe, bufs)
+    for rep in range(2):
+        for k in range(3):
+            step.submit(k)
+        for k in range(3):
+            e, g = step.result(k)
+            xe = bufs[k].to(dev).permute(0, 2, 1).requires_grad_(True)
+            ee = tpe.energy_per_conformation(xe)
+            ee.sum().backward()
+            assert torch.equal(e, ee.detach().cpu()) and torch.equal(g, xe.grad.permute(0, 2, 1).cpu()), (rep, k)
+        bufs[1].add_(0.01)                                              # the loader writes new batches into the same pinned buffers
+        bufs[2].mul_(1.001)
+    with pytest.raises(ValueError):
+        GraphedEnergyStep(tpe, [x0])                                    # not pinned
