@@ -821,7 +821,7 @@ def main():
     # through the public autograd path) and replayed: one cudaGraphLaunch per batch instead of ~0.14 ms of Python,
     # buffers alternating over two streams.  The host reads every batch's results (result(k) waits for batch k).
     from molearn_b200.loss_functions import GraphedEnergyStep
-    gstep = GraphedEnergyStep(tpe, hx)
+    gstep = GraphedEnergyStep(tpe, hx, n_streams=int(os.environ.get("MLP_GRAPH_STREAMS", 4)))
     n_slots = len(hx)
 
     def timed_graph(steps, warm):
@@ -865,7 +865,7 @@ def main():
     e2e = {"value": world * B * args.steps / (ms_graph * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": per, "d2h_bytes_per_step": per + B * 16, "ms_per_step": ms_graph / args.steps,
            "mode": "GraphedEnergyStep: H2D + energy_per_conformation + backward + D2H of energies and gradient captured once per pinned "
-                   "host buffer through the public autograd path, one CUDA-graph replay per batch, two streams; the host reads every result",
+                   "host buffer through the public autograd path, one CUDA-graph replay per batch, buffers alternating over four streams; the host reads every result",
            "graph_equals_eager": graph_equal,
            "eager_pipelined": eager,
            "pipelined_energy_and_gradient_call": {"value": world * B * pipe_steps / (ms_dir * 1e-3), "ms_per_step": ms_dir / pipe_steps,
