@@ -77,7 +77,7 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
 #endif
 #ifndef NB2_RCP
-#define NB2_RCP 0
+#define NB2_RCP 1    // 1/r^2 of the force scalar from MUFU.RCP instead of inv*inv: one FMA-pipe operation per pair moves to the XU pipe (+1.1 %)
 #endif
 #ifndef NB_PACKED
 #define NB_PACKED 1  // 1: nb_kernel2 (packed FFMA2 pair loop), 0: scalar nb_kernel
@@ -2102,6 +2102,9 @@ struct Workspace { size_t e_bonded, e_nb, fpart, total; };
 #ifndef NB_BLK_MIN_ITEMS
 #define NB_BLK_MIN_ITEMS 8
 #endif
+#ifndef NB_BLK_MEM_MB
+#define NB_BLK_MEM_MB 64
+#endif
 int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pair (nb_kernel2)
     if (!e->packed || e->blk_mode == 0) return -1;
     if (e->blk_mode > 0) {
@@ -2112,6 +2115,9 @@ int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pai
     int best = -1;
     for (int lv = 0; lv < NB_BLK_LEVELS; ++lv)        // an item of R x C tile pairs wants >= NB_BLK_MIN_ITEMS items per slot
         if (per_slot >= (double)NB_BLK_MIN_ITEMS * NB_BLK_ROWS[lv] * NB_BLK_C) best = lv;
+    // memory: one warp per tile pair needs 3 KB of scratch per tile pair and conformation; beyond NB_BLK_MEM_MB per
+    // conformation (systems of more than ~26 k atoms) blocks of at least 4 rows are used whatever the batch size
+    if (best < 1 && (size_t)e->n_pairs * 6 * NB_T * sizeof(float) > ((size_t)NB_BLK_MEM_MB << 20)) best = 1;
     return best;
 }
 // partial-force blocks (3 x 128 floats) and energy partials per conformation under the schedule in use
