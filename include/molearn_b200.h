@@ -146,6 +146,11 @@ int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B, uint32_t term
  * pairs, masked NB tile pairs, padded atom count. */
 int mlp_energy_info(const mlp_energy* e, int64_t info[8]);
 
+/* Lennard-Jones classes (distinct (R, eps) of utils.py:814-815, plus one zero class for the padding atoms) when the
+ * repulsive pair kernel reads w_ij^2 = ((12 eps_ij)^(1/12) R_ij)^2 from its type-pair table in shared memory, 0 when
+ * it computes w_ij per pair (more than 7 classes, NB = 'full', or MLP_NB_LUT=0 in the environment at create time). */
+int mlp_energy_nb_table_classes(const mlp_energy* e);
+
 /* Energies and (optionally) gradient of B <= 65535 conformations.
  *
  *   x          dev, logical shape [B,3,N] fp32 addressed as x[b*sxb + c*sxc + n*sxn]

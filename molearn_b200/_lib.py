@@ -30,6 +30,7 @@ SYMBOLS = {
     "mlp_energy_destroy": (None, [c_void_p]),
     "mlp_energy_workspace_bytes": (c_int64, [c_void_p, c_int64, c_uint32, c_int]),
     "mlp_energy_info": (c_int, [c_void_p, c_void_p]),
+    "mlp_energy_nb_table_classes": (c_int, [c_void_p]),
     "mlp_energy_eval": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                 c_void_p, c_int64, c_int64, c_int64, c_void_p, c_uint32, c_uint32,
                                 c_void_p, c_int64, c_void_p]),

@@ -133,6 +133,12 @@ struct mlp_energy {
     float2* d_parw = nullptr;      // [Npad] (a, b) product-form LJ parameters of the packed repulsive kernel
     float* d_q = nullptr;          // [Npad]
     float2* d_par = nullptr;       // [Npad] (R/2, sqrt(12 eps))
+    // type-pair table of the repulsive mode (systems with few Lennard-Jones classes): w_ij^2 looked up, not computed
+    bool lut_on = false;           // MLP_NB_LUT=0 switches it off
+    int lut_classes = 0, lut_n = 0; // classes incl. the zero class of the padding atoms; table entries (classes^3)
+    uint32_t* d_lrow = nullptr;    // [Npad] byte offset of the atom's table row
+    uint2* d_lpc = nullptr;        // [Npad/4] byte offsets, within a row, of the group's two j-atom pairs
+    float2* d_lut = nullptr;       // [c][c][c] (w^2(ci, cj0), w^2(ci, cj1))
     int* d_red_off = nullptr;      // [n_nbt+1] per tile: range in d_red_list
     int* d_red_list = nullptr;     // entries pair*2 + side (0: the tile is the pair's I, 1: its J)
     // block-item schedules of the pair term (nb_block_kernel): used when there is much more work than warp slots;
@@ -148,6 +154,7 @@ struct mlp_energy {
     int2* d_pair_meta = nullptr;         // [nt(nt+1)/2] (mask index | -1, step bits) of tile pair (I, J >= I)
     float* d_tpar = nullptr;             // [nt][3][128] charge, R/2, sqrt(12 eps)
     float* d_tparw = nullptr;            // [nt][3][128] charge, a, b (product form of the repulsive mode)
+    float* d_tparl = nullptr;            // [nt][320] charge, table row offsets, pair offsets (table form of the repulsive mode)
     int last_launches = 0;
     int sm_count = 148;
     // side stream: the (latency-bound) bonded kernel runs next to the non-bonded pair kernel
@@ -485,11 +492,12 @@ constexpr float NB_MASKED_R2 = 1.0e4f;  // stand-in r^2 of statically excluded p
 
 // Fast-path pair term at squared distance r2c >= NB_THR2.  Returns s = -(dE/dd)/d; adds 12*E_lj to
 // Sl and E_coulomb to Sc.
-template <bool FULL>
+// W2 (type-pair table form of the repulsive mode, nb_micro2<.., LUT>): Rij holds w_ij^2 and e12 = 1.
+template <bool FULL, bool W2 = false>
 __device__ __forceinline__ float nb_pair_fast(float r2c, float Rij, float e12, float qq, float& Sl, float& Sc) {
     float inv = rsqrt_fast(r2c);
     float t = Rij * inv;
-    float t2 = t * t;
+    float t2 = W2 ? Rij * rcp_fast(r2c) : t * t;
     float t6 = t2 * t2 * t2;
     float u6 = e12 * t6;
     float ec = qq * inv;
@@ -497,7 +505,7 @@ __device__ __forceinline__ float nb_pair_fast(float r2c, float Rij, float e12, f
     if (FULL) { u = fmaf(u6, t6 - 1.f, ec); Sl = fmaf(u6, t6 - 2.f, Sl); }
     else { u = fmaf(u6, t6, ec); Sl = fmaf(u6, t6, Sl); }
     Sc = fmaf(qq, inv, Sc);
-    return u * (inv * inv);
+    return W2 ? u * rcp_fast(r2c) : u * (inv * inv);
 }
 
 // Exact pair term (any distance), minus what the fast path added for this pair at the clamped
@@ -514,10 +522,10 @@ __device__ __forceinline__ float nb_pair_fast(float r2c, float Rij, float e12, f
 #else
 #define NB_FIX_ATTR __noinline__
 #endif
-template <bool FULL>
+template <bool FULL, bool W2 = false>
 __device__ NB_FIX_ATTR float3 nb_pair_fix(float r2, float Rij, float e12, float qq) {
     float Sl_f = 0.f, Sc_f = 0.f;
-    float s_f = nb_pair_fast<FULL>(NB_THR2, Rij, e12, qq, Sl_f, Sc_f);
+    float s_f = nb_pair_fast<FULL, W2>(NB_THR2, Rij, e12, qq, Sl_f, Sc_f);
     // the fast path multiplied s by the true (dx,dy,dz); so must the correction.
     // Lean arithmetic (a collapsed decode sends most pairs through here): rsqrt + Newton for d, ex2.approx for the
     // two elu branches (|d - k| < 2: 2 ulp), rcp.approx for 1/w (1 ulp, x12 in the LJ term = 7e-7).
@@ -529,7 +537,7 @@ __device__ NB_FIX_ATTR float3 nb_pair_fix(float r2, float Rij, float e12, float 
     float w2 = far2 ? d : ex2 - 1.f + C_K, dw2 = far2 ? 1.f : ex2;
     float iw1 = rcp_fast(w1), iw2 = rcp_fast(w2);
     float t = Rij * iw1;
-    float t2 = t * t;
+    float t2 = W2 ? Rij * (iw1 * iw1) : t * t;
     float t6 = t2 * t2 * t2;
     float u6 = e12 * t6;
     float ec = qq * iw2;
@@ -543,9 +551,16 @@ __device__ NB_FIX_ATTR float3 nb_pair_fix(float r2, float Rij, float e12, float 
 // One micro-tile: NB_NI i-atoms (registers) x 4 j-atoms, fast path with clamped distance.
 // m16: bit (4a+b) = pair allowed (MASKED tiles).  Returns true if any allowed pair is closer than
 // sqrt(NB_THR2) or not comparable (NaN coordinates) - the caller then runs the exact correction.
+#ifndef NB_RMIN3
+#define NB_RMIN3 0   // 1: one three-input FMNMX3 per two pairs; 0: two FMNMX.NAN (the three-input form issues at a lower rate: -1 % kernel time)
+#endif
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
+#if NB_RMIN3
     asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // sm_100 three-input min (one FMNMX3); NaN wins
+#else
+    asm("{ .reg .f32 t; min.NaN.f32 t, %2, %3; min.NaN.f32 %0, %1, t; }" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // NaN wins
+#endif
     return r;
 }
 
@@ -585,10 +600,13 @@ __device__ __forceinline__ bool nb_micro(const float4 (&xi)[NB_NI], const float2
 
 // Correction pass over a micro-tile that holds at least one pair closer than sqrt(NB_THR2).
 // WFORM: the per-atom parameters are (a, b) of nb_micro2's product form, R_ij (12 eps_ij)^(1/12) = a_i b_j + b_i a_j.
-template <bool MASKED, bool FULL, bool WFORM = false>
+// PFORM 2: the table form - w2m[a][b] holds w_ij^2 of the pair (pi / pj are not read).
+template <bool MASKED, bool FULL, int PFORM = 0>
 __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const float2 (&pi)[NB_NI], const float4 (&xj)[4],
                                              const float2 (&pj)[4], uint32_t m16,
-                                             float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc) {
+                                             float3 (&Fi)[NB_NI], float3 (&Fj)[4], float& Sl, float& Sc,
+                                             const float (*w2m)[4] = nullptr) {
+    constexpr bool WFORM = PFORM == 1;
     // Launder the operands: without this the compiler shares dx/r2/... with the hot micro-tile
     // and keeps 60+ values alive (spilled to local memory) just in case this path runs.
     float4 yi[NB_NI], yj[4];
@@ -611,9 +629,9 @@ __device__ __forceinline__ void nb_micro_fix(const float4 (&xi)[NB_NI], const fl
             bool on = !MASKED || ((m16 >> (4 * a + b)) & 1u);
             // NaN coordinates: !(r2 >= thr) is true -> exact path -> NaN propagates
             if (on && !(r2 >= NB_THR2)) {
-                const float Rij = WFORM ? fmaf(pi[a].y, pj[b].x, pi[a].x * pj[b].y) : pi[a].x + pj[b].x;
-                const float e12 = WFORM ? 1.f : pi[a].y * pj[b].y;
-                float3 c = nb_pair_fix<FULL>(r2, Rij, e12, yi[a].w * yj[b].w);
+                const float Rij = PFORM == 2 ? w2m[a][b] : WFORM ? fmaf(pi[a].y, pj[b].x, pi[a].x * pj[b].y) : pi[a].x + pj[b].x;
+                const float e12 = PFORM ? 1.f : pi[a].y * pj[b].y;
+                float3 c = nb_pair_fix<FULL, PFORM == 2>(r2, Rij, e12, yi[a].w * yj[b].w);
                 Fi[a].x = fmaf(c.x, dx, Fi[a].x); Fi[a].y = fmaf(c.x, dy, Fi[a].y); Fi[a].z = fmaf(c.x, dz, Fi[a].z);
                 Fj[b].x = fmaf(c.x, dx, Fj[b].x); Fj[b].y = fmaf(c.x, dy, Fj[b].y); Fj[b].z = fmaf(c.x, dz, Fj[b].z);
                 Sl += c.y; Sc += c.z;
@@ -741,6 +759,12 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
 #ifndef NB_DIAG_SPLIT
 #define NB_DIAG_SPLIT 2
 #endif
+#ifndef NB_STEP_UNROLL
+#define NB_STEP_UNROLL 1   // rotation steps per trip of the pair loop
+#endif
+#ifndef NB_KO
+#define NB_KO 0      // knock-out experiments (wrong results; tools/nb_variants.sh): 1 no clamp, 2 no r_min, 4 no rotation, 8 no energy sums, 16 1/r^2 = inv^2, 32 no MUFU, 64 table value not loaded
+#endif
 #ifndef NB_WFORM
 #define NB_WFORM 1
 #endif
@@ -788,10 +812,23 @@ __device__ __forceinline__ float fsum(fval F) { return F.x + F.y; }
 __device__ __forceinline__ void faddlo(fval& F, float v) { F.x += v; }
 #endif
 
-template <bool GRAD, bool MASKED, bool FULL>
+// LUT (repulsive mode, few Lennard-Jones classes): w_ij^2 of the two packed pairs comes from a shared-memory table
+// indexed by (class of the i-atom, classes of the j-atom pair) - one IADD + one LDS.64 instead of three packed
+// FMA-pipe operations (w_ij: 2, t = w/d: 1): (w/d)^2 = w_ij^2 * rcp(r^2), 21 FMA-pipe operations per pair instead of 24.
+// lrow[a]: byte offset of the table row of i-atom a; pc: byte offsets of the lane's two j-atom pairs within a row.
+struct NbLut { const char* base; uint32_t lrow[NB_NI]; uint2 pc; };
+__device__ __forceinline__ float2 nb_lut_w2(const NbLut& L, int a, int p) {
+#if NB_KO & 64
+    return make_float2(__uint_as_float(L.lrow[a]), __uint_as_float(p ? L.pc.y : L.pc.x));
+#endif
+    return *reinterpret_cast<const float2*>(L.base + (L.lrow[a] + (p ? L.pc.y : L.pc.x)));
+}
+
+template <bool GRAD, bool MASKED, bool FULL, bool LUT = false>
 __device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival (&hRi)[NB_NI], const ival (&sei)[NB_NI],
                                            const float4 (&cj)[6], uint32_t m16,
-                                           fval (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
+                                           fval (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc, const NbLut& L) {
+    static_assert(!(LUT && FULL), "the table form is the repulsive mode's");
     constexpr bool WF = NB_WFORM && !FULL;
     float rmin = 3.0e38f;
     const float2 neg1 = dup(-1.f), one = dup(1.f);
@@ -807,10 +844,10 @@ __device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival
         for (int a = 0; a < NB_NI; ++a) {
             float2 dx = isub(xj, xi[a][0]), dy = isub(yj, xi[a][1]), dz = isub(zj, xi[a][2]);
             float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-            // WF: (hRi, sei) = (a_i, b_i), (hj, sj) = (a_j, b_j); e12 holds w_ij
-            float2 e12 = WF ? ifma(sei[a], hj, imul(hRi[a], sj)) : imul(sei[a], sj);
+            // WF: (hRi, sei) = (a_i, b_i), (hj, sj) = (a_j, b_j); e12 holds w_ij.  LUT: Rij holds w_ij^2 (e12 unused)
+            float2 e12 = LUT ? dup(1.f) : WF ? ifma(sei[a], hj, imul(hRi[a], sj)) : imul(sei[a], sj);
             float2 qq = imul(xi[a][3], qj);
-            float2 Rij = WF ? e12 : iadd(hRi[a], hj);
+            float2 Rij = LUT ? nb_lut_w2(L, a, p) : WF ? e12 : iadd(hRi[a], hj);
             if (MASKED) {
                 const bool on0 = (m16 >> (4 * a + 2 * p)) & 1u, on1 = (m16 >> (4 * a + 2 * p + 1)) & 1u;
                 r2.x = on0 ? r2.x : NB_MASKED_R2; r2.y = on1 ? r2.y : NB_MASKED_R2;
@@ -818,11 +855,29 @@ __device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival
                 else { e12.x = on0 ? e12.x : 0.f; e12.y = on1 ? e12.y : 0.f; }
                 qq.x = on0 ? qq.x : 0.f; qq.y = on1 ? qq.y : 0.f;
             }
+#if NB_KO & 2
+            rmin = r2.x;
+#else
             rmin = fmin3(rmin, r2.x, r2.y);
+#endif
+#if NB_KO & 1
+            const float2 r2c = r2;
+#else
             const float2 r2c = f2(fmaxf(r2.x, NB_THR2), fmaxf(r2.y, NB_THR2));
+#endif
+#if NB_KO & 32
+            float2 inv = __fmul2_rn(r2c, dup(0.01f));
+#else
             float2 inv = f2(rsqrt_fast(r2c.x), rsqrt_fast(r2c.y));
-            float2 t = __fmul2_rn(Rij, inv);
-            float2 t2 = __fmul2_rn(t, t);
+#endif
+            float2 rinv2 = dup(0.f);
+            float2 t2;
+#if NB_KO & 48
+            if (LUT) { rinv2 = __fmul2_rn(inv, inv); t2 = __fmul2_rn(Rij, rinv2); }
+#else
+            if (LUT) { rinv2 = f2(rcp_fast(r2c.x), rcp_fast(r2c.y)); t2 = __fmul2_rn(Rij, rinv2); }
+#endif
+            else { const float2 t = __fmul2_rn(Rij, inv); t2 = __fmul2_rn(t, t); }
             float2 t6 = __fmul2_rn(__fmul2_rn(t2, t2), t2);
             float2 u6 = WF ? t6 : __fmul2_rn(e12, t6);
             float2 ec = __fmul2_rn(qq, inv);
@@ -832,14 +887,18 @@ __device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival
                 Sl = __ffma2_rn(u6, __ffma2_rn(t6, one, dup(-2.f)), Sl);
             } else {
                 u = __ffma2_rn(u6, t6, ec);
+#if !(NB_KO & 8)
                 Sl = __ffma2_rn(u6, t6, Sl);
+#endif
             }
+#if !(NB_KO & 8)
             Sc = __ffma2_rn(qq, inv, Sc);
+#endif
             if (GRAD) {
 #if NB2_RCP
-                float2 s = __fmul2_rn(u, f2(rcp_fast(r2c.x), rcp_fast(r2c.y)));   // 1/r^2 on the (idle) MUFU pipe
+                float2 s = __fmul2_rn(u, LUT ? rinv2 : f2(rcp_fast(r2c.x), rcp_fast(r2c.y)));   // 1/r^2 on the (idle) MUFU pipe
 #else
-                float2 s = __fmul2_rn(u, __fmul2_rn(inv, inv));
+                float2 s = __fmul2_rn(u, LUT ? rinv2 : __fmul2_rn(inv, inv));
 #endif
                 facc(Fi[a][0], s, dx); facc(Fi[a][1], s, dy); facc(Fi[a][2], s, dz);
                 Fj[p][0] = __ffma2_rn(s, dx, Fj[p][0]); Fj[p][1] = __ffma2_rn(s, dy, Fj[p][1]); Fj[p][2] = __ffma2_rn(s, dz, Fj[p][2]);
@@ -859,10 +918,10 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return r;
 }
 
-template <bool GRAD, bool MASKED, bool FULL>
+template <bool GRAD, bool MASKED, bool FULL, bool LUT = false>
 __device__ __forceinline__ bool nb_micro2_exact(const ival (&xi)[NB_NI][4], const ival (&hRi)[NB_NI], const ival (&sei)[NB_NI],
                                                  const float4 (&cj)[6], uint32_t m16,
-                                                 fval (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc) {
+                                                 fval (&Fi)[NB_NI][3], float2 (&Fj)[2][3], float2& Sl, float2& Sc, const NbLut& L) {
     constexpr bool WF = NB_WFORM && !FULL;
     constexpr float LOG2E = 1.4426950408889634f;
     float rmin = 3.0e38f;
@@ -879,9 +938,9 @@ __device__ __forceinline__ bool nb_micro2_exact(const ival (&xi)[NB_NI][4], cons
         for (int a = 0; a < NB_NI; ++a) {
             float2 dx = isub(xj, xi[a][0]), dy = isub(yj, xi[a][1]), dz = isub(zj, xi[a][2]);
             float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-            float2 e12 = WF ? ifma(sei[a], hj, imul(hRi[a], sj)) : imul(sei[a], sj);
+            float2 e12 = LUT ? dup(1.f) : WF ? ifma(sei[a], hj, imul(hRi[a], sj)) : imul(sei[a], sj);
             float2 qq = imul(xi[a][3], qj);
-            float2 Rij = WF ? e12 : iadd(hRi[a], hj);
+            float2 Rij = LUT ? nb_lut_w2(L, a, p) : WF ? e12 : iadd(hRi[a], hj);
             if (MASKED) {
                 const bool on0 = (m16 >> (4 * a + 2 * p)) & 1u, on1 = (m16 >> (4 * a + 2 * p + 1)) & 1u;
                 r2.x = on0 ? r2.x : NB_MASKED_R2; r2.y = on1 ? r2.y : NB_MASKED_R2;
@@ -905,7 +964,7 @@ __device__ __forceinline__ bool nb_micro2_exact(const ival (&xi)[NB_NI][4], cons
             const float2 iw = f2(rcp_fast(ww.x), rcp_fast(ww.y));
             const float2 iw1 = __fmul2_rn(iw, w2), iw2 = __fmul2_rn(iw, w1);
             const float2 t = __fmul2_rn(Rij, iw1);
-            const float2 t2 = __fmul2_rn(t, t);
+            const float2 t2 = LUT ? __fmul2_rn(Rij, __fmul2_rn(iw1, iw1)) : __fmul2_rn(t, t);
             const float2 t6 = __fmul2_rn(__fmul2_rn(t2, t2), t2);
             const float2 u6 = WF ? t6 : __fmul2_rn(e12, t6);
             const float2 ec = __fmul2_rn(qq, iw2);
@@ -930,14 +989,19 @@ __device__ __forceinline__ bool nb_micro2_exact(const ival (&xi)[NB_NI][4], cons
     return !(rmin >= NB_THR2);
 }
 
-template <bool GRAD, bool FULL>
+template <bool GRAD, bool FULL, bool LUT>
 __global__ void __launch_bounds__(32, 4 * NB2_MINB)
 nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const float* __restrict__ q, int N,
            const float2* __restrict__ par, const int4* __restrict__ pairs,
            const uint32_t* __restrict__ masks, const uint32_t* __restrict__ stepbits, int n_pairs, int B,
-           float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
-    __shared__ float4 s_j[6][32];                 // component c of the 128 j-atoms: s_j[c][g] = atoms 4g..4g+3
-    __shared__ uint32_t s_m[NB_T * 4];            // uint16 [g][lane] pair masks, as words
+           float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part,
+           const uint32_t* __restrict__ lrow /* [Npad] */, const uint2* __restrict__ lpc /* [Npad/4] */,
+           const float2* __restrict__ lut, int lut_n) {
+    constexpr int NC = LUT ? 4 : 6;                // LUT: (x, y, z, q) only; the pair codes replace the two LJ parameters
+    __shared__ float4 s_j[NC][32];                 // component c of the 128 j-atoms: s_j[c][g] = atoms 4g..4g+3
+    __shared__ uint2 s_pc[LUT ? 32 : 1];           // LUT: table offsets of the two j-atom pairs of group g
+    __shared__ uint32_t s_m[NB_T * 4];             // uint16 [g][lane] pair masks, as words
+    extern __shared__ __align__(16) float2 s_lut[];   // LUT: [class i][class j0][class j1] -> (w^2(i,j0), w^2(i,j1))
     const int lane = threadIdx.x;
     const long work = blockIdx.x;
     const int p = (int)(work / B), b = (int)(work - (long)p * B);
@@ -950,12 +1014,24 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
 
     ival xi[NB_NI][4], hRi[NB_NI], sei[NB_NI];
     fval Fi[NB_NI][3];
+    NbLut L;
+    L.base = reinterpret_cast<const char*>(s_lut);
+    L.pc = make_uint2(0u, 0u);
+    if (LUT) {
+        const uint4 r4 = reinterpret_cast<const uint4*>(lrow + i0)[lane];
+        L.lrow[0] = r4.x; L.lrow[1] = r4.y; L.lrow[2] = r4.z; L.lrow[3] = r4.w;
+        for (int k = lane; k < lut_n; k += 32) s_lut[k] = lut[k];
+        s_pc[lane] = lpc[(j0 >> 2) + lane];
+    }
 #pragma unroll
     for (int a = 0; a < NB_NI; ++a) {
         const float4 v = nb_load_atom(xb, sxc, sxn, q, i0 + 4 * lane + a, N);
-        const float2 pr = par[i0 + 4 * lane + a];
         xi[a][0] = imake(v.x); xi[a][1] = imake(v.y); xi[a][2] = imake(v.z); xi[a][3] = imake(v.w);
-        hRi[a] = imake(pr.x); sei[a] = imake(pr.y);
+        if (!LUT) {
+            const float2 pr = par[i0 + 4 * lane + a];
+            hRi[a] = imake(pr.x); sei[a] = imake(pr.y);
+            L.lrow[a] = 0u;
+        } else hRi[a] = sei[a] = imake(0.f);
         Fi[a][0] = Fi[a][1] = Fi[a][2] = fzero();
     }
     {
@@ -964,9 +1040,11 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         for (int k = 0; k < NB_T / 32; ++k) {
             const int jj = lane + 32 * k;
             const float4 v = nb_load_atom(xb, sxc, sxn, q, j0 + jj, N);
-            const float2 pr = par[j0 + jj];
             sf[0 * NB_T + jj] = v.x; sf[1 * NB_T + jj] = v.y; sf[2 * NB_T + jj] = v.z; sf[3 * NB_T + jj] = v.w;
-            sf[4 * NB_T + jj] = pr.x; sf[5 * NB_T + jj] = pr.y;
+            if (!LUT) {
+                const float2 pr = par[j0 + jj];
+                sf[4 * NB_T + jj] = pr.x; sf[5 * NB_T + jj] = pr.y;
+            }
         }
     }
     if (masked) {
@@ -992,21 +1070,26 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         float4 ui[NB_NI], uj[4];
         float2 upi[NB_NI], upj[4];
         float3 dFi[NB_NI], dFj[4];
+        float w2m[NB_NI][4];
         float dSl = 0.f, dSc = 0.f;
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) {
             ui[a] = make_float4(ilo(xi[a][0]), ilo(xi[a][1]), ilo(xi[a][2]), ilo(xi[a][3]));
             upi[a] = make_float2(ilo(hRi[a]), ilo(sei[a]));
             dFi[a] = make_float3(0.f, 0.f, 0.f);
+            if (LUT) {
+                const float2 w0 = nb_lut_w2(L, a, 0), w1 = nb_lut_w2(L, a, 1);
+                w2m[a][0] = w0.x; w2m[a][1] = w0.y; w2m[a][2] = w1.x; w2m[a][3] = w1.y;
+            }
         }
         const float* cf = reinterpret_cast<const float*>(cj);
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
             uj[bb] = make_float4(cf[0 * 4 + bb], cf[1 * 4 + bb], cf[2 * 4 + bb], cf[3 * 4 + bb]);
-            upj[bb] = make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
+            upj[bb] = LUT ? make_float2(0.f, 0.f) : make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
             dFj[bb] = make_float3(0.f, 0.f, 0.f);
         }
-        nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+        nb_micro_fix<true, FULL, LUT ? 2 : (NB_WFORM && !FULL)>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc, w2m);
 #pragma unroll
         for (int a = 0; a < NB_NI; ++a) { faddlo(Fi[a][0], dFi[a].x); faddlo(Fi[a][1], dFi[a].y); faddlo(Fi[a][2], dFi[a].z); }
         Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
@@ -1016,7 +1099,7 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         Sl.x += dSl; Sc.x += dSc;
     };
     auto rotate = [&]() {
-        if (GRAD) {
+        if (GRAD && !(NB_KO & 4)) {
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp)
 #pragma unroll
@@ -1027,16 +1110,18 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         }
     };
     int r = r_begin;
-#pragma unroll 1
+    constexpr int kStepUnroll = NB_STEP_UNROLL;
+#pragma unroll kStepUnroll
     for (; r < n_steps; ++r) {
         const int g = (lane + r) & 31;
         float4 cj[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) cj[c] = s_j[c][g];
+        for (int c = 0; c < NC; ++c) cj[c] = s_j[c][g];
+        if (LUT) { L.pc = s_pc[g]; cj[4] = cj[5] = make_float4(0.f, 0.f, 0.f, 0.f); }
         const bool mstep = (sbits >> r) & 1u;
         const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
-        const bool close = mstep ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
-                                  : nb_micro2<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+        const bool close = mstep ? nb_micro2<GRAD, true, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L)
+                                  : nb_micro2<GRAD, false, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L);
         if (close) fix_tile(cj, m16);
         rotate();
         // collapsed structures (an untrained decoder's output): when at least half of the lanes met a close pair in the
@@ -1048,11 +1133,12 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         const int g = (lane + r) & 31;
         float4 cj[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) cj[c] = s_j[c][g];
+        for (int c = 0; c < NC; ++c) cj[c] = s_j[c][g];
+        if (LUT) { L.pc = s_pc[g]; cj[4] = cj[5] = make_float4(0.f, 0.f, 0.f, 0.f); }
         const bool mstep = (sbits >> r) & 1u;
         const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
-        if (mstep) nb_micro2_exact<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
-        else nb_micro2_exact<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+        if (mstep) nb_micro2_exact<GRAD, true, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L);
+        else nb_micro2_exact<GRAD, false, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L);
         rotate();
     }
     if (GRAD) {
@@ -1086,6 +1172,9 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
 // Items are either rectangles strictly above the diagonal band (R <= NB_BLK_R, C <= NB_BLK_C) or single rows
 // (R = 1: the diagonal tile and the tiles up to the next rectangle).  Scratch per conformation drops from
 // 3 KB x tile pairs to about 1.5 KB x tile pairs x (1/R + 1/C).
+#ifndef NB_LUT_MAXC
+#define NB_LUT_MAXC 7   // most Lennard-Jones classes the table form is used for (8^3 entries of 8 bytes = 4 KB per warp)
+#endif
 #define NB_BLK_R 8    // largest block height (NB_BLK_ROWS)
 #ifndef NB_BLK_C
 #define NB_BLK_C 4
@@ -1103,13 +1192,17 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-template <bool GRAD, bool FULL>
+template <bool GRAD, bool FULL, bool LUT>
 __global__ void __launch_bounds__(32, 4 * NB2_MINB)
 nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N, int nt,
-                const float* __restrict__ tpar /* [nt][3][128]: charge, then the two per-atom LJ parameters */,
+                const float* __restrict__ tpar /* [nt][3][128]: charge, then the two per-atom LJ parameters; LUT: [nt][320] charge,
+                                                   table row offsets of the 128 atoms, pair offsets of the 32 groups */,
                 const NbBlockItem* __restrict__ items, const int2* __restrict__ pair_meta /* [nt(nt+1)/2]: mask index | -1, step bits */,
                 const uint32_t* __restrict__ masks, int n_items, int n_blocks, int B,
-                float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part) {
+                float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part,
+                const float2* __restrict__ lut, int lut_n, int acc_floats) {
+    constexpr int TPW = LUT ? NB_T + NB_T + NB_T / 2 : 3 * NB_T;   // words of per-tile parameters
+    constexpr int NC = LUT ? 4 : 6;
     __shared__ __align__(16) float s_j[2][6 * NB_T];          // double buffer: component c of the 128 j-atoms at [c*128 + jj]
     __shared__ __align__(16) uint32_t s_m[2][NB_T * 4];       // uint16 [g][lane] pair masks of a masked tile, as words
     extern __shared__ __align__(16) float s_acc[];            // [C][3][128] j-force accumulators of a rectangle (R > 1)
@@ -1145,9 +1238,14 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
                 dst[jj] = 1.0e6f + 100.f * (float)(n - N); dst[NB_T + jj] = -1.0e6f; dst[2 * NB_T + jj] = 1.0e6f;
             }
         }
-        const float* src = tpar + (long)J * (3 * NB_T);
+        const float* src = tpar + (long)J * TPW;
+        if (LUT) {      // charges of the 128 atoms, then the pair offsets of the 32 groups (skipping the row offsets)
+            cp_async16(dst + 3 * NB_T + 4 * lane, src + 4 * lane);
+            if (lane < 16) cp_async16(dst + 4 * NB_T + 4 * lane, src + 2 * NB_T + 4 * lane);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) cp_async16(dst + 3 * NB_T + 4 * (lane + 32 * k), src + 4 * (lane + 32 * k));
+            for (int k = 0; k < 3; ++k) cp_async16(dst + 3 * NB_T + 4 * (lane + 32 * k), src + 4 * (lane + 32 * k));
+        }
         const int mi = s_meta[t].x;
         if (mi >= 0) {
             const uint32_t* ms = masks + (long)mi * (NB_T * 4);
@@ -1160,6 +1258,13 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
     if (n_tile > 1) issue(1, 1); else cp_async_commit();
 
     float2 Sl = dup(0.f), Sc = dup(0.f);
+    NbLut L{};
+    if (LUT) {       // the type-pair table sits behind the j-force accumulators
+        float2* s_lut = reinterpret_cast<float2*>(s_acc + acc_floats);
+        for (int k = lane; k < lut_n; k += 32) s_lut[k] = lut[k];
+        L.base = reinterpret_cast<const char*>(s_lut);
+        __syncwarp();
+    }
     ival xi[NB_NI][4], hRi[NB_NI], sei[NB_NI];
     fval Fi[NB_NI][3];
     const int src_lane = (lane + 1) & 31;
@@ -1167,16 +1272,17 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
     for (int r = 0; r < it.R; ++r) {
         const int I = it.I0 + r, i0 = I * NB_T;
         {
-            const float4* tp = reinterpret_cast<const float4*>(tpar + (long)I * (3 * NB_T));
-            const float4 q4 = tp[lane], h4 = tp[32 + lane], s4 = tp[64 + lane];
+            const float4* tp = reinterpret_cast<const float4*>(tpar + (long)I * TPW);
+            const float4 q4 = tp[lane], h4 = tp[32 + lane], s4 = LUT ? h4 : tp[64 + lane];
             const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, hv[4] = {h4.x, h4.y, h4.z, h4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            if (LUT) { L.lrow[0] = __float_as_uint(h4.x); L.lrow[1] = __float_as_uint(h4.y); L.lrow[2] = __float_as_uint(h4.z); L.lrow[3] = __float_as_uint(h4.w); }
 #pragma unroll
             for (int a = 0; a < NB_NI; ++a) {
                 const int n = i0 + 4 * lane + a;
                 float vx = 1.0e6f + 100.f * (float)(n - N), vy = -1.0e6f, vz = 1.0e6f;
                 if (n < N) { const float* p = xb + (long)n * sxn; vx = p[0]; vy = p[sxc]; vz = p[2 * sxc]; }
                 xi[a][0] = imake(vx); xi[a][1] = imake(vy); xi[a][2] = imake(vz); xi[a][3] = imake(qv[a]);
-                hRi[a] = imake(hv[a]); sei[a] = imake(sv[a]);
+                hRi[a] = imake(LUT ? 0.f : hv[a]); sei[a] = imake(LUT ? 0.f : sv[a]);
                 Fi[a][0] = Fi[a][1] = Fi[a][2] = fzero();
             }
         }
@@ -1190,6 +1296,7 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
             const int n_steps = (J == I) ? 17 : 32;            // diagonal tile: block (L,g) mirrors (g,L)
             const float4(*sj)[32] = reinterpret_cast<const float4(*)[32]>(s_j[buf]);
             const uint16_t* sm16 = reinterpret_cast<const uint16_t*>(s_m[buf]);
+            const uint2* spc = reinterpret_cast<const uint2*>(s_j[buf] + 4 * NB_T);
             float2 Fj[2][3];
 #pragma unroll
             for (int pp = 0; pp < 2; ++pp) Fj[pp][0] = Fj[pp][1] = Fj[pp][2] = dup(0.f);
@@ -1197,21 +1304,26 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
                 float4 ui[NB_NI], uj[4];
                 float2 upi[NB_NI], upj[4];
                 float3 dFi[NB_NI], dFj[4];
+                float w2m[NB_NI][4];
                 float dSl = 0.f, dSc = 0.f;
 #pragma unroll
                 for (int a = 0; a < NB_NI; ++a) {
                     ui[a] = make_float4(ilo(xi[a][0]), ilo(xi[a][1]), ilo(xi[a][2]), ilo(xi[a][3]));
                     upi[a] = make_float2(ilo(hRi[a]), ilo(sei[a]));
                     dFi[a] = make_float3(0.f, 0.f, 0.f);
+                    if (LUT) {
+                        const float2 w0 = nb_lut_w2(L, a, 0), w1 = nb_lut_w2(L, a, 1);
+                        w2m[a][0] = w0.x; w2m[a][1] = w0.y; w2m[a][2] = w1.x; w2m[a][3] = w1.y;
+                    }
                 }
                 const float* cf = reinterpret_cast<const float*>(cj);
 #pragma unroll
                 for (int bb = 0; bb < 4; ++bb) {
                     uj[bb] = make_float4(cf[0 * 4 + bb], cf[1 * 4 + bb], cf[2 * 4 + bb], cf[3 * 4 + bb]);
-                    upj[bb] = make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
+                    upj[bb] = LUT ? make_float2(0.f, 0.f) : make_float2(cf[4 * 4 + bb], cf[5 * 4 + bb]);
                     dFj[bb] = make_float3(0.f, 0.f, 0.f);
                 }
-                nb_micro_fix<true, FULL, NB_WFORM && !FULL>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc);
+                nb_micro_fix<true, FULL, LUT ? 2 : (NB_WFORM && !FULL)>(ui, upi, uj, upj, m16, dFi, dFj, dSl, dSc, w2m);
 #pragma unroll
                 for (int a = 0; a < NB_NI; ++a) { faddlo(Fi[a][0], dFi[a].x); faddlo(Fi[a][1], dFi[a].y); faddlo(Fi[a][2], dFi[a].z); }
                 Fj[0][0].x += dFj[0].x; Fj[0][1].x += dFj[0].y; Fj[0][2].x += dFj[0].z;
@@ -1237,11 +1349,12 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
                 const int g = (lane + rs) & 31;
                 float4 cj[6];
 #pragma unroll
-                for (int cc = 0; cc < 6; ++cc) cj[cc] = sj[cc][g];
+                for (int cc = 0; cc < NC; ++cc) cj[cc] = sj[cc][g];
+                if (LUT) { L.pc = spc[g]; cj[4] = cj[5] = make_float4(0.f, 0.f, 0.f, 0.f); }
                 const bool mstep = (sbits >> rs) & 1u;
                 const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
-                const bool close = mstep ? nb_micro2<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc)
-                                         : nb_micro2<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+                const bool close = mstep ? nb_micro2<GRAD, true, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L)
+                                         : nb_micro2<GRAD, false, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L);
                 if (close) fix_tile(cj, m16);
                 rotate();
                 if (NB_DENSE_MODE && rs == 0 && __popc(__ballot_sync(0xffffffffu, close)) >= 16) { ++rs; break; }
@@ -1251,11 +1364,12 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
                 const int g = (lane + rs) & 31;
                 float4 cj[6];
 #pragma unroll
-                for (int cc = 0; cc < 6; ++cc) cj[cc] = sj[cc][g];
+                for (int cc = 0; cc < NC; ++cc) cj[cc] = sj[cc][g];
+                if (LUT) { L.pc = spc[g]; cj[4] = cj[5] = make_float4(0.f, 0.f, 0.f, 0.f); }
                 const bool mstep = (sbits >> rs) & 1u;
                 const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
-                if (mstep) nb_micro2_exact<GRAD, true, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
-                else nb_micro2_exact<GRAD, false, FULL>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc);
+                if (mstep) nb_micro2_exact<GRAD, true, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L);
+                else nb_micro2_exact<GRAD, false, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L);
                 rotate();
             }
             if (GRAD) {
@@ -1965,6 +2079,50 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
         const double bw = std::pow(12.0 * (double)T.vdw_e[i], 1.0 / 24.0);   // 0 for eps = 0
         parw[i] = make_float2((float)(bw * 0.5 * (double)T.vdw_R[i]), (float)bw);
     }
+    std::vector<uint32_t> lut_lrow;
+    std::vector<uint2> lut_lpc;
+    // Lennard-Jones classes: atoms with the same (R, eps).  Up to NB_LUT_MAXC classes (plus a zero class for the
+    // padding atoms) the repulsive kernel reads w_ij^2 = ((12 eps_ij)^(1/12) R_ij)^2 from a table in shared memory.
+    {
+        std::map<std::pair<float, float>, int> cls;
+        std::vector<int> c_of(E->Npad, 0);
+        for (int i = 0; i < N; ++i) {
+            auto key = std::make_pair(T.vdw_R[i], T.vdw_e[i]);
+            auto it = cls.find(key);
+            if (it == cls.end()) it = cls.emplace(key, (int)cls.size()).first;
+            c_of[i] = it->second;
+        }
+        const int C = (int)cls.size() + 1;
+        for (int i = N; i < E->Npad; ++i) c_of[i] = C - 1;
+        E->lut_classes = C;
+        E->lut_on = false;
+        if (C <= NB_LUT_MAXC + 1) {
+            std::vector<double> R(C, 0.0), ep(C, 0.0);
+            for (auto& kv : cls) { R[kv.second] = kv.first.first; ep[kv.second] = kv.first.second; }
+            auto w2 = [&](int a, int b) {
+                if (a == C - 1 || b == C - 1) return 0.f;
+                const double w = std::pow(12.0 * std::sqrt(ep[a] * ep[b]), 1.0 / 12.0) * 0.5 * (R[a] + R[b]);
+                return (float)(w * w);
+            };
+            std::vector<float2> lut((size_t)C * C * C);
+            for (int a = 0; a < C; ++a)
+                for (int b0 = 0; b0 < C; ++b0)
+                    for (int b1 = 0; b1 < C; ++b1) lut[((size_t)a * C + b0) * C + b1] = make_float2(w2(a, b0), w2(a, b1));
+            std::vector<uint32_t> lrow(E->Npad);
+            std::vector<uint2> lpc(E->Npad / 4);
+            for (int i = 0; i < E->Npad; ++i) lrow[i] = (uint32_t)c_of[i] * C * C * (uint32_t)sizeof(float2);
+            for (int g = 0; g < E->Npad / 4; ++g)
+                lpc[g] = make_uint2((uint32_t)(c_of[4 * g] * C + c_of[4 * g + 1]) * (uint32_t)sizeof(float2),
+                                    (uint32_t)(c_of[4 * g + 2] * C + c_of[4 * g + 3]) * (uint32_t)sizeof(float2));
+            E->lut_n = (int)lut.size();
+            int rc;
+            if ((rc = upload(E, &E->d_lut, lut))) return rc;
+            if ((rc = upload(E, &E->d_lrow, lrow))) return rc;
+            if ((rc = upload(E, &E->d_lpc, lpc))) return rc;
+            lut_lrow = lrow; lut_lpc = lpc;
+            E->lut_on = true;
+        }
+    }
     // exclusions per tile pair
     std::map<std::pair<int, int>, std::vector<std::pair<int, int>>> ex;
     for (size_t k = 0; k < T.excl.size() / 2; ++k) {
@@ -2039,6 +2197,17 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
         const size_t o = (size_t)(n / NB_T) * 3 * NB_T + n % NB_T;
         tpar[o] = q[n]; tpar[o + NB_T] = par[n].x; tpar[o + 2 * NB_T] = par[n].y;
         tparw[o] = q[n]; tparw[o + NB_T] = parw[n].x; tparw[o + 2 * NB_T] = parw[n].y;
+    }
+    if (E->lut_on) {     // per tile: 128 charges, 128 table row offsets, 32 x 2 pair offsets
+        constexpr int TPW = NB_T + NB_T + NB_T / 2;
+        std::vector<float> tparl((size_t)nt * TPW);
+        for (int t = 0; t < nt; ++t) {
+            float* o = tparl.data() + (size_t)t * TPW;
+            for (int k = 0; k < NB_T; ++k) { o[k] = q[t * NB_T + k]; std::memcpy(o + NB_T + k, &lut_lrow[t * NB_T + k], 4); }
+            std::memcpy(o + 2 * NB_T, &lut_lpc[(size_t)t * (NB_T / 4)], (NB_T / 4) * sizeof(uint2));
+        }
+        int rcl;
+        if ((rcl = upload(E, &E->d_tparl, tparl))) return rcl;
     }
     std::vector<int2> pair_meta((size_t)nt * (nt + 1) / 2, make_int2(-1, 0));
     auto pid = [&](int I, int J) { return (size_t)I * nt - (size_t)I * (I - 1) / 2 + (J - I); };
@@ -2203,6 +2372,7 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
         if (const char* env = std::getenv("MLP_NB_FIRST")) E->nb_first = std::atoi(env) != 0;
         if (const char* env = std::getenv("MLP_NB_BLOCKS")) E->blk_mode = std::max(0, std::atoi(env));   // 0: never, 2/4/8: always that block height
         if (const char* env = std::getenv("MLP_NB_PACKED")) E->packed = std::atoi(env) != 0;
+        if (const char* env = std::getenv("MLP_NB_LUT")) E->lut_on = E->lut_on && std::atoi(env) != 0;
         if (cudaStreamCreateWithFlags(&E->side, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&E->ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -2253,6 +2423,8 @@ int mlp_energy_info(const mlp_energy* e, int64_t info[8]) {
     info[4] = e->n_nbt; info[5] = e->n_pairs; info[6] = e->n_masked; info[7] = e->Npad;
     return MLP_OK;
 }
+
+int mlp_energy_nb_table_classes(const mlp_energy* e) { return (e && e->lut_on && e->nb_mode != MLP_NB_FULL) ? e->lut_classes : 0; }
 
 int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B, uint32_t term_mask, int want_grad) {
     if (!e || B < 0) return MLP_E_ARG;
@@ -2386,18 +2558,20 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         const bool full = e->nb_mode == MLP_NB_FULL;
         double* ep = energies ? e_nb : nullptr;
 #define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
-#define NB_LAUNCH2(G, F) nb_kernel2<G, F><<<(unsigned)items, 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, (int)B, fpart, weights, ep)
+#define NB_LAUNCH2(G, F, T) nb_kernel2<G, F, T><<<(unsigned)items, 32, T ? e->lut_n * sizeof(float2) : 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, (int)B, fpart, weights, ep, e->d_lrow, e->d_lpc, e->d_lut, e->lut_n)
         const int lv = block_level(e, B);
         const bool blocks_on = lv >= 0;
         const mlp_energy::BlockSchedule& S = e->blk[blocks_on ? lv : 0];
-#define NB_LAUNCHB(G, F) nb_block_kernel<G, F><<<(unsigned)((long)B * S.items), 32, e->blk_acc_smem, stream>>>(x, sxb, sxc, sxn, N, e->n_nbt, \
-            (NB_WFORM && !F) ? e->d_tparw : e->d_tpar, S.d_items, e->d_pair_meta, e->d_masks, S.items, S.blocks, (int)B, fpart, weights, ep)
+#define NB_LAUNCHB(G, F, T) nb_block_kernel<G, F, T><<<(unsigned)((long)B * S.items), 32, e->blk_acc_smem + (T ? e->lut_n * sizeof(float2) : 0), stream>>>(x, sxb, sxc, sxn, N, e->n_nbt, \
+            T ? e->d_tparl : (NB_WFORM && !F) ? e->d_tparw : e->d_tpar, S.d_items, e->d_pair_meta, e->d_masks, S.items, S.blocks, (int)B, fpart, weights, ep, \
+            e->d_lut, e->lut_n, e->blk_acc_smem / (int)sizeof(float))
+        const bool tab = !full && e->lut_on;
         if (blocks_on) {
-            if (grad) { if (full) NB_LAUNCHB(true, true); else NB_LAUNCHB(true, false); }
-            else { if (full) NB_LAUNCHB(false, true); else NB_LAUNCHB(false, false); }
+            if (grad) { if (full) NB_LAUNCHB(true, true, false); else if (tab) NB_LAUNCHB(true, false, true); else NB_LAUNCHB(true, false, false); }
+            else { if (full) NB_LAUNCHB(false, true, false); else if (tab) NB_LAUNCHB(false, false, true); else NB_LAUNCHB(false, false, false); }
         } else if (e->packed) {
-            if (grad) { if (full) NB_LAUNCH2(true, true); else NB_LAUNCH2(true, false); }
-            else { if (full) NB_LAUNCH2(false, true); else NB_LAUNCH2(false, false); }
+            if (grad) { if (full) NB_LAUNCH2(true, true, false); else if (tab) NB_LAUNCH2(true, false, true); else NB_LAUNCH2(true, false, false); }
+            else { if (full) NB_LAUNCH2(false, true, false); else if (tab) NB_LAUNCH2(false, false, true); else NB_LAUNCH2(false, false, false); }
         } else {
             if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
             else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }

@@ -109,7 +109,9 @@ class _DeviceEnergy:
         _lib.check(_lib.lib().mlp_energy_info(self._h, v.ctypes.data_as(ctypes.c_void_p)))
         keys = ("bonded_tiles", "bonded_tile_atoms", "max_contributions_per_atom", "bonded_smem_bytes",
                 "nb_tiles", "nb_tile_pairs", "nb_masked_tile_pairs", "n_atoms_padded")
-        return dict(zip(keys, (int(a) for a in v)))
+        out = dict(zip(keys, (int(a) for a in v)))
+        out["nb_table_classes"] = int(_lib.lib().mlp_energy_nb_table_classes(self._h))   # 0: w_ij computed per pair
+        return out
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

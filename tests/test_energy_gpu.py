@@ -402,7 +402,7 @@ def test_conformation_extent_limit_is_reported(dev, energy_objs, golden_energy):
 
 
 @pytest.mark.parametrize("knob", ["MLP_NB_PACKED=0", "MLP_NO_OVERLAP=1", "MLP_BONDED_TILE=64", "MLP_BONDED_TILE=40", "MLP_NB_BLOCKS=8", "MLP_NB_BLOCKS=2",
-                                  "MLP_NB_FIRST=1"])
+                                  "MLP_NB_FIRST=1", "MLP_NB_LUT=0"])
 def test_alternative_code_paths_agree(knob, dev, golden_topo, golden_energy, monkeypatch):
     """The library's run-time switches (read when a handle is created) select other code paths of the same maths: the
     scalar pair kernel, no side-stream overlap, smaller bonded tiles (other work-item matchings and halos).  Each must
@@ -413,6 +413,8 @@ def test_alternative_code_paths_agree(knob, dev, golden_topo, golden_energy, mon
     tpe = TorchProteinEnergy(None, atominfo_from(golden_topo("bbcb")), device=dev)
     if name == "MLP_BONDED_TILE":
         assert tpe._dev().info()["bonded_tile_atoms"] == int(value)
+    # backbone + CB has four Lennard-Jones classes (+ the padding class): the type-pair table is the default path
+    assert tpe._dev().info()["nb_table_classes"] == (0 if name == "MLP_NB_LUT" else 5)
     en = golden_energy("bbcb")
     gf = list(en["grad_frames"])
     x = torch.from_numpy(en["x"][gf]).to(dev).permute(0, 2, 1)
