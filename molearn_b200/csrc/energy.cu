@@ -76,6 +76,9 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #ifndef NB2_MINB
 #define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
 #endif
+#ifndef NB2_MINB_LUT
+#define NB2_MINB_LUT 4   // the table form needs fewer registers: four resident warps per sub-partition (128 registers) - equal at MurD x 64, +2 % at 10 k atoms
+#endif
 #ifndef NB2_RCP
 #define NB2_RCP 1    // 1/r^2 of the force scalar from MUFU.RCP instead of inv*inv: one FMA-pipe operation per pair moves to the XU pipe (+1.1 %)
 #endif
@@ -759,6 +762,9 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
 #ifndef NB_DIAG_SPLIT
 #define NB_DIAG_SPLIT 2
 #endif
+#ifndef NB_REUSE_ORDER
+#define NB_REUSE_ORDER 1   // source order / operand choice that lets consecutive FFMA2s share operands (operand reuse cache)
+#endif
 #ifndef NB_STEP_UNROLL
 #define NB_STEP_UNROLL 1   // rotation steps per trip of the pair loop
 #endif
@@ -892,7 +898,11 @@ __device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival
 #endif
             }
 #if !(NB_KO & 8)
+#if NB_REUSE_ORDER
+            Sc = __ffma2_rn(ec, one, Sc);      // two register pairs read instead of three (qq, inv, Sc)
+#else
             Sc = __ffma2_rn(qq, inv, Sc);
+#endif
 #endif
             if (GRAD) {
 #if NB2_RCP
@@ -900,8 +910,15 @@ __device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival
 #else
                 float2 s = __fmul2_rn(u, LUT ? rinv2 : __fmul2_rn(inv, inv));
 #endif
+#if NB_REUSE_ORDER
+                // the i- and the j-side accumulation of a component share two of their three operands
+                facc(Fi[a][0], s, dx); Fj[p][0] = __ffma2_rn(s, dx, Fj[p][0]);
+                facc(Fi[a][1], s, dy); Fj[p][1] = __ffma2_rn(s, dy, Fj[p][1]);
+                facc(Fi[a][2], s, dz); Fj[p][2] = __ffma2_rn(s, dz, Fj[p][2]);
+#else
                 facc(Fi[a][0], s, dx); facc(Fi[a][1], s, dy); facc(Fi[a][2], s, dz);
                 Fj[p][0] = __ffma2_rn(s, dx, Fj[p][0]); Fj[p][1] = __ffma2_rn(s, dy, Fj[p][1]); Fj[p][2] = __ffma2_rn(s, dz, Fj[p][2]);
+#endif
             }
         }
     }
@@ -990,7 +1007,7 @@ __device__ __forceinline__ bool nb_micro2_exact(const ival (&xi)[NB_NI][4], cons
 }
 
 template <bool GRAD, bool FULL, bool LUT>
-__global__ void __launch_bounds__(32, 4 * NB2_MINB)
+__global__ void __launch_bounds__(32, 4 * (LUT ? NB2_MINB_LUT : NB2_MINB))
 nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const float* __restrict__ q, int N,
            const float2* __restrict__ par, const int4* __restrict__ pairs,
            const uint32_t* __restrict__ masks, const uint32_t* __restrict__ stepbits, int n_pairs, int B,
@@ -1003,8 +1020,10 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     __shared__ uint32_t s_m[NB_T * 4];             // uint16 [g][lane] pair masks, as words
     extern __shared__ __align__(16) float2 s_lut[];   // LUT: [class i][class j0][class j1] -> (w^2(i,j0), w^2(i,j1))
     const int lane = threadIdx.x;
-    const long work = blockIdx.x;
-    const int p = (int)(work / B), b = (int)(work - (long)p * B);
+    // grid (B, y, z): conformation in x, tile pair p = z * gridDim.y + y - the launch order (x fastest) is the pair-major
+    // order of the item list (longest first), without an integer division in every warp
+    const int b = blockIdx.x, p = blockIdx.z * gridDim.y + blockIdx.y;
+    if (p >= n_pairs) return;
     if (weights && !e_part && weights[4 * b + 3] == 0.f) return;
     const int4 IJ = pairs[p];
     const long item = (long)b * n_pairs + p;
@@ -1023,9 +1042,18 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
         for (int k = lane; k < lut_n; k += 32) s_lut[k] = lut[k];
         s_pc[lane] = lpc[(j0 >> 2) + lane];
     }
+    // Element offsets inside one conformation are 32-bit (mlp_energy_eval checks the extent) and are stepped by
+    // additions: the prologue of an item runs next to two warps that keep the FMA pipe busy, where every IMAD of a
+    // 64-bit "n * stride" waited for the pipe (12 % of the kernel's warp-time was spent on 45 such instructions).
+    const int sn = (int)sxn, sc = (int)sxc;
+    const float* pi = xb + (i0 + 4 * lane) * sn;
+    const float4 qi4 = reinterpret_cast<const float4*>(q + i0)[lane];
+    const float qiv[4] = {qi4.x, qi4.y, qi4.z, qi4.w};
 #pragma unroll
-    for (int a = 0; a < NB_NI; ++a) {
-        const float4 v = nb_load_atom(xb, sxc, sxn, q, i0 + 4 * lane + a, N);
+    for (int a = 0; a < NB_NI; ++a, pi += sn) {
+        const int n = i0 + 4 * lane + a;
+        float4 v = make_float4(1.0e6f + 100.f * (float)(n - N), -1.0e6f, 1.0e6f, 0.f);   // padding atoms: parked far away (nb_load_atom)
+        if (n < N) { const float* pc = pi + sc; v = make_float4(pi[0], pc[0], pc[sc], qiv[a]); }
         xi[a][0] = imake(v.x); xi[a][1] = imake(v.y); xi[a][2] = imake(v.z); xi[a][3] = imake(v.w);
         if (!LUT) {
             const float2 pr = par[i0 + 4 * lane + a];
@@ -1036,10 +1064,13 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     }
     {
         float* sf = reinterpret_cast<float*>(s_j);
+        const float* pj = xb + (j0 + lane) * sn;
+        const int sn32 = sn << 5;
 #pragma unroll
-        for (int k = 0; k < NB_T / 32; ++k) {
-            const int jj = lane + 32 * k;
-            const float4 v = nb_load_atom(xb, sxc, sxn, q, j0 + jj, N);
+        for (int k = 0; k < NB_T / 32; ++k, pj += sn32) {
+            const int jj = lane + 32 * k, n = j0 + jj;
+            float4 v = make_float4(1.0e6f + 100.f * (float)(n - N), -1.0e6f, 1.0e6f, 0.f);
+            if (n < N) { const float* pc = pj + sc; v = make_float4(pj[0], pc[0], pc[sc], q[n]); }
             sf[0 * NB_T + jj] = v.x; sf[1 * NB_T + jj] = v.y; sf[2 * NB_T + jj] = v.z; sf[3 * NB_T + jj] = v.w;
             if (!LUT) {
                 const float2 pr = par[j0 + jj];
@@ -1175,6 +1206,9 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
 #ifndef NB_LUT_MAXC
 #define NB_LUT_MAXC 7   // most Lennard-Jones classes the table form is used for (8^3 entries of 8 bytes = 4 KB per warp)
 #endif
+#ifndef NB2B_MINB
+#define NB2B_MINB NB2_MINB   // block-item kernel: resident warps per SM sub-partition the register budget is sized for
+#endif
 #define NB_BLK_R 8    // largest block height (NB_BLK_ROWS)
 #ifndef NB_BLK_C
 #define NB_BLK_C 4
@@ -1193,7 +1227,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 template <bool GRAD, bool FULL, bool LUT>
-__global__ void __launch_bounds__(32, 4 * NB2_MINB)
+__global__ void __launch_bounds__(32, 4 * (LUT ? NB2_MINB_LUT : NB2B_MINB))
 nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N, int nt,
                 const float* __restrict__ tpar /* [nt][3][128]: charge, then the two per-atom LJ parameters; LUT: [nt][320] charge,
                                                    table row offsets of the 128 atoms, pair offsets of the 32 groups */,
@@ -1208,9 +1242,10 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
     extern __shared__ __align__(16) float s_acc[];            // [C][3][128] j-force accumulators of a rectangle (R > 1)
     __shared__ int2 s_meta[32];                                // (mask index | -1, step bits) of the item's tiles
     const int lane = threadIdx.x;
-    const long work = blockIdx.x;
-    const int q = (int)(work / B), b = (int)(work - (long)q * B);
+    const int b = blockIdx.x, q = blockIdx.z * gridDim.y + blockIdx.y;   // grid (B, y, z): item-major launch order, no integer division
+    if (q >= n_items) return;
     if (weights && !e_part && weights[4 * b + 3] == 0.f) return;
+    const int sn = (int)sxn, sc = (int)sxc, sn32 = sn << 5;   // 32-bit element offsets, stepped by additions (see nb_kernel2)
     const NbBlockItem it = items[q];
     const float* xb = x + (long)b * sxb;
     const int n_tile = it.R * it.C;
@@ -1228,12 +1263,13 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
         const int J = it.J0 + t % it.C;
         const int j0 = J * NB_T;
         float* dst = s_j[buf];
+        const float* p = xb + (j0 + lane) * sn;
 #pragma unroll
-        for (int k = 0; k < NB_T / 32; ++k) {
+        for (int k = 0; k < NB_T / 32; ++k, p += sn32) {
             const int jj = lane + 32 * k, n = j0 + jj;
             if (n < N) {
-                const float* p = xb + (long)n * sxn;
-                cp_async4(dst + jj, p); cp_async4(dst + NB_T + jj, p + sxc); cp_async4(dst + 2 * NB_T + jj, p + 2 * sxc);
+                const float* pc = p + sc;
+                cp_async4(dst + jj, p); cp_async4(dst + NB_T + jj, pc); cp_async4(dst + 2 * NB_T + jj, pc + sc);
             } else {   // padding of the last tile: parked far away (zero charge / LJ parameters in tpar)
                 dst[jj] = 1.0e6f + 100.f * (float)(n - N); dst[NB_T + jj] = -1.0e6f; dst[2 * NB_T + jj] = 1.0e6f;
             }
@@ -1276,11 +1312,12 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
             const float4 q4 = tp[lane], h4 = tp[32 + lane], s4 = LUT ? h4 : tp[64 + lane];
             const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, hv[4] = {h4.x, h4.y, h4.z, h4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
             if (LUT) { L.lrow[0] = __float_as_uint(h4.x); L.lrow[1] = __float_as_uint(h4.y); L.lrow[2] = __float_as_uint(h4.z); L.lrow[3] = __float_as_uint(h4.w); }
+            const float* p = xb + (i0 + 4 * lane) * sn;
 #pragma unroll
-            for (int a = 0; a < NB_NI; ++a) {
+            for (int a = 0; a < NB_NI; ++a, p += sn) {
                 const int n = i0 + 4 * lane + a;
                 float vx = 1.0e6f + 100.f * (float)(n - N), vy = -1.0e6f, vz = 1.0e6f;
-                if (n < N) { const float* p = xb + (long)n * sxn; vx = p[0]; vy = p[sxc]; vz = p[2 * sxc]; }
+                if (n < N) { const float* pc = p + sc; vx = p[0]; vy = pc[0]; vz = pc[sc]; }
                 xi[a][0] = imake(vx); xi[a][1] = imake(vy); xi[a][2] = imake(vz); xi[a][3] = imake(qv[a]);
                 hRi[a] = imake(LUT ? 0.f : hv[a]); sei[a] = imake(LUT ? 0.f : sv[a]);
                 Fi[a][0] = Fi[a][1] = Fi[a][2] = fzero();
@@ -2280,7 +2317,8 @@ int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pai
         for (int lv = 0; lv < NB_BLK_LEVELS; ++lv) if (NB_BLK_ROWS[lv] == e->blk_mode) return lv;
         return NB_BLK_LEVELS - 1;
     }
-    const double per_slot = (double)e->n_nbt * (e->n_nbt + 1) / 2 * (double)B / ((double)e->sm_count * 4 * NB2_MINB);
+    const bool tab = e->lut_on && e->nb_mode != MLP_NB_FULL;
+    const double per_slot = (double)e->n_nbt * (e->n_nbt + 1) / 2 * (double)B / ((double)e->sm_count * 4 * (tab ? NB2_MINB_LUT : NB2_MINB));
     int best = -1;
     for (int lv = 0; lv < NB_BLK_LEVELS; ++lv)        // an item of R x C tile pairs wants >= NB_BLK_MIN_ITEMS items per slot
         if (per_slot >= (double)NB_BLK_MIN_ITEMS * NB_BLK_ROWS[lv] * NB_BLK_C) best = lv;
@@ -2558,11 +2596,13 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         const bool full = e->nb_mode == MLP_NB_FULL;
         double* ep = energies ? e_nb : nullptr;
 #define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
-#define NB_LAUNCH2(G, F, T) nb_kernel2<G, F, T><<<(unsigned)items, 32, T ? e->lut_n * sizeof(float2) : 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, (int)B, fpart, weights, ep, e->d_lrow, e->d_lpc, e->d_lut, e->lut_n)
+#define NB_LAUNCH2(G, F, T) nb_kernel2<G, F, T><<<grid2, 32, T ? e->lut_n * sizeof(float2) : 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, (int)B, fpart, weights, ep, e->d_lrow, e->d_lpc, e->d_lut, e->lut_n)
+        const unsigned gy = (unsigned)std::min(e->n_pairs, 65535);
+        const dim3 grid2((unsigned)B, gy, (unsigned)((e->n_pairs + gy - 1) / gy));
         const int lv = block_level(e, B);
         const bool blocks_on = lv >= 0;
         const mlp_energy::BlockSchedule& S = e->blk[blocks_on ? lv : 0];
-#define NB_LAUNCHB(G, F, T) nb_block_kernel<G, F, T><<<(unsigned)((long)B * S.items), 32, e->blk_acc_smem + (T ? e->lut_n * sizeof(float2) : 0), stream>>>(x, sxb, sxc, sxn, N, e->n_nbt, \
+#define NB_LAUNCHB(G, F, T) nb_block_kernel<G, F, T><<<dim3((unsigned)B, (unsigned)std::min(S.items, 65535), (unsigned)((S.items + 65534) / 65535)), 32, e->blk_acc_smem + (T ? e->lut_n * sizeof(float2) : 0), stream>>>(x, sxb, sxc, sxn, N, e->n_nbt, \
             T ? e->d_tparl : (NB_WFORM && !F) ? e->d_tparw : e->d_tpar, S.d_items, e->d_pair_meta, e->d_masks, S.items, S.blocks, (int)B, fpart, weights, ep, \
             e->d_lut, e->lut_n, e->blk_acc_smem / (int)sizeof(float))
         const bool tab = !full && e->lut_on;
