@@ -153,7 +153,8 @@ struct mlp_energy {
         int* d_red_list = nullptr;
     } blk[NB_BLK_LEVELS];
     int blk_acc_smem = 0;                // dynamic shared memory of a block-item CTA (j-force accumulators)
-    int blk_mode = -1;                   // -1: by work per warp slot, 0: never, R: always the level with R rows (MLP_NB_BLOCKS)
+    int blk_mode = -1;                   // -1: by scratch per conformation, 0: never, R: always the level with R rows (MLP_NB_BLOCKS)
+    int ws_cap_mb = 0;                   // partial-force scratch of one pair launch (MLP_NB_WS_MB; batches are evaluated in chunks)
     int2* d_pair_meta = nullptr;         // [nt(nt+1)/2] (mask index | -1, step bits) of tile pair (I, J >= I)
     float* d_tpar = nullptr;             // [nt][3][128] charge, R/2, sqrt(12 eps)
     float* d_tparw = nullptr;            // [nt][3][128] charge, a, b (product form of the repulsive mode)
@@ -169,6 +170,7 @@ struct mlp_energy {
     // optional per-kernel timing (mlp_energy_profile): events on the launching stream
     bool profile = false;
     std::vector<std::array<cudaEvent_t, 2>> pending[4];  // per kernel: (start, stop) pairs not read yet
+    std::vector<char> pending_first[4];                   // 0: a further chunk of the same call (its time is added, the call is counted once)
     double prof_ms[4] = {0, 0, 0, 0};
     long prof_n[4] = {0, 0, 0, 0};
     std::vector<void*> allocs;
@@ -2302,14 +2304,22 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
 
 struct Workspace { size_t e_bonded, e_nb, fpart, total; };
 
-// The pair term runs as block items (nb_block_kernel) when every resident warp slot gets at least NB_BLK_MIN_ITEMS
-// items of the block size; below that the one-tile-pair items of nb_kernel2 balance the SMs better.  A pure function of the
-// handle and the batch size: mlp_energy_workspace_bytes and mlp_energy_eval agree on it.
+// Schedule of the pair term.  One warp per tile pair (nb_kernel2) is the faster kernel at every size measured (MurD x 64,
+// 10 715 atoms x 32 / 128, 51 432 atoms x 8: 10-12 % ahead of the block items since the table form and the lean item
+// prologue), but it needs 3 KB of partial forces per tile pair and conformation.  Two bounds keep that scratch O(N):
+//   * a batch is evaluated in chunks of conformations whose partial forces fit NB_WS_CAP_MB (MLP_NB_WS_MB; each chunk is
+//     one pair launch + one reduction, and a chunk of one 10 k-atom conformation is already 1.5 waves of warps);
+//   * when ONE conformation needs more than NB_BLK_MEM_MB (systems beyond ~26 k atoms) the block items are used: rows in
+//     registers, column forces accumulated in shared memory, about a fifth of the scratch.
+// A pure function of the handle and the batch size: mlp_energy_workspace_bytes and mlp_energy_eval agree on it.
 #ifndef NB_BLK_MIN_ITEMS
 #define NB_BLK_MIN_ITEMS 8
 #endif
 #ifndef NB_BLK_MEM_MB
 #define NB_BLK_MEM_MB 64
+#endif
+#ifndef NB_WS_CAP_MB
+#define NB_WS_CAP_MB 384
 #endif
 int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pair (nb_kernel2)
     if (!e->packed || e->blk_mode == 0) return -1;
@@ -2317,19 +2327,25 @@ int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pai
         for (int lv = 0; lv < NB_BLK_LEVELS; ++lv) if (NB_BLK_ROWS[lv] == e->blk_mode) return lv;
         return NB_BLK_LEVELS - 1;
     }
+    if ((size_t)e->n_pairs * 6 * NB_T * sizeof(float) <= ((size_t)NB_BLK_MEM_MB << 20)) return -1;
+    // memory-bound regime: the biggest blocks that still leave every resident warp slot NB_BLK_MIN_ITEMS items, at least 4 rows
     const bool tab = e->lut_on && e->nb_mode != MLP_NB_FULL;
     const double per_slot = (double)e->n_nbt * (e->n_nbt + 1) / 2 * (double)B / ((double)e->sm_count * 4 * (tab ? NB2_MINB_LUT : NB2_MINB));
-    int best = -1;
-    for (int lv = 0; lv < NB_BLK_LEVELS; ++lv)        // an item of R x C tile pairs wants >= NB_BLK_MIN_ITEMS items per slot
+    int best = 1;
+    for (int lv = 1; lv < NB_BLK_LEVELS; ++lv)
         if (per_slot >= (double)NB_BLK_MIN_ITEMS * NB_BLK_ROWS[lv] * NB_BLK_C) best = lv;
-    // memory: one warp per tile pair needs 3 KB of scratch per tile pair and conformation; beyond NB_BLK_MEM_MB per
-    // conformation (systems of more than ~26 k atoms) blocks of at least 4 rows are used whatever the batch size
-    if (best < 1 && (size_t)e->n_pairs * 6 * NB_T * sizeof(float) > ((size_t)NB_BLK_MEM_MB << 20)) best = 1;
     return best;
 }
 // partial-force blocks (3 x 128 floats) and energy partials per conformation under the schedule in use
 int nb_blocks(const mlp_energy* e, int64_t B) { const int lv = block_level(e, B); return lv >= 0 ? e->blk[lv].blocks : 2 * e->n_pairs; }
 int nb_eparts(const mlp_energy* e, int64_t B) { const int lv = block_level(e, B); return lv >= 0 ? e->blk[lv].items : e->n_pairs; }
+
+// conformations per pair launch: the partial forces of a chunk fit the scratch cap (at least one conformation)
+int64_t nb_chunk(const mlp_energy* e, int64_t B) {
+    const size_t per = (size_t)nb_blocks(e, B) * 3 * NB_T * sizeof(float);
+    const int64_t c = (int64_t)(((size_t)e->ws_cap_mb << 20) / std::max<size_t>(per, 1));
+    return std::max<int64_t>(1, std::min<int64_t>(B, c));
+}
 
 Workspace layout(const mlp_energy* e, int64_t B, uint32_t term_mask, bool grad) {
     Workspace w{};
@@ -2338,7 +2354,7 @@ Workspace layout(const mlp_energy* e, int64_t B, uint32_t term_mask, bool grad) 
     w.e_nb = off;
     if (term_mask & MLP_TERM_NB) off += align256((size_t)B * nb_eparts(e, B) * sizeof(double));
     w.fpart = off;
-    if ((term_mask & MLP_TERM_NB) && grad) off += align256((size_t)B * nb_blocks(e, B) * 3 * NB_T * sizeof(float));
+    if ((term_mask & MLP_TERM_NB) && grad) off += align256((size_t)nb_chunk(e, B) * nb_blocks(e, B) * 3 * NB_T * sizeof(float));
     w.total = off + 256;
     return w;
 }
@@ -2408,6 +2424,8 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
     if (rc == MLP_OK) {
         if (const char* env = std::getenv("MLP_NO_OVERLAP")) E->overlap = std::atoi(env) == 0;
         if (const char* env = std::getenv("MLP_NB_FIRST")) E->nb_first = std::atoi(env) != 0;
+        E->ws_cap_mb = NB_WS_CAP_MB;
+        if (const char* env = std::getenv("MLP_NB_WS_MB")) E->ws_cap_mb = std::max(1, std::atoi(env));
         if (const char* env = std::getenv("MLP_NB_BLOCKS")) E->blk_mode = std::max(0, std::atoi(env));   // 0: never, 2/4/8: always that block height
         if (const char* env = std::getenv("MLP_NB_PACKED")) E->packed = std::atoi(env) != 0;
         if (const char* env = std::getenv("MLP_NB_LUT")) E->lut_on = E->lut_on && std::atoi(env) != 0;
@@ -2484,10 +2502,11 @@ int mlp_energy_profile_read(mlp_energy* e, double ms[4], int64_t counts[4]) {
             CK(cudaEventSynchronize(p[1]));
             float t = 0.f;
             CK(cudaEventElapsedTime(&t, p[0], p[1]));
-            e->prof_ms[k] += t; e->prof_n[k] += 1;
+            e->prof_ms[k] += t;
             cudaEventDestroy(p[0]); cudaEventDestroy(p[1]);
         }
-        e->pending[k].clear();
+        for (char f : e->pending_first[k]) e->prof_n[k] += f ? 1 : 0;
+        e->pending[k].clear(); e->pending_first[k].clear();
         ms[k] = e->prof_ms[k]; counts[k] = e->prof_n[k];
         e->prof_ms[k] = 0; e->prof_n[k] = 0;
     }
@@ -2542,12 +2561,13 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
     const bool bonded = term_mask & MLP_TERM_BONDED, nonbonded = term_mask & MLP_TERM_NB;
     int launches = 0;
 
-    auto prof_begin = [&](int k) {
+    auto prof_begin = [&](int k, bool first = true) {
         if (!e->profile) return;
         std::array<cudaEvent_t, 2> p;
         cudaEventCreate(&p[0]); cudaEventCreate(&p[1]);
         cudaEventRecord(p[0], stream);
         e->pending[k].push_back(p);
+        e->pending_first[k].push_back(first ? 1 : 0);
     };
     auto prof_end = [&](int k) { if (e->profile) cudaEventRecord(e->pending[k].back()[1], stream); };
 
@@ -2590,53 +2610,62 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         ++launches;
     }
     if (nonbonded) {
-        prof_begin(2);
-        long items = (long)B * e->n_pairs;
-        unsigned blocks = (unsigned)((items + NB_WARPS - 1) / NB_WARPS);
         const bool full = e->nb_mode == MLP_NB_FULL;
-        double* ep = energies ? e_nb : nullptr;
-#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, (int)B, fpart, weights, ep)
-#define NB_LAUNCH2(G, F, T) nb_kernel2<G, F, T><<<grid2, 32, T ? e->lut_n * sizeof(float2) : 0, stream>>>(x, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, (int)B, fpart, weights, ep, e->d_lrow, e->d_lpc, e->d_lut, e->lut_n)
-        const unsigned gy = (unsigned)std::min(e->n_pairs, 65535);
-        const dim3 grid2((unsigned)B, gy, (unsigned)((e->n_pairs + gy - 1) / gy));
         const int lv = block_level(e, B);
         const bool blocks_on = lv >= 0;
         const mlp_energy::BlockSchedule& S = e->blk[blocks_on ? lv : 0];
-#define NB_LAUNCHB(G, F, T) nb_block_kernel<G, F, T><<<dim3((unsigned)B, (unsigned)std::min(S.items, 65535), (unsigned)((S.items + 65534) / 65535)), 32, e->blk_acc_smem + (T ? e->lut_n * sizeof(float2) : 0), stream>>>(x, sxb, sxc, sxn, N, e->n_nbt, \
-            T ? e->d_tparl : (NB_WFORM && !F) ? e->d_tparw : e->d_tpar, S.d_items, e->d_pair_meta, e->d_masks, S.items, S.blocks, (int)B, fpart, weights, ep, \
-            e->d_lut, e->lut_n, e->blk_acc_smem / (int)sizeof(float))
         const bool tab = !full && e->lut_on;
-        if (blocks_on) {
-            if (grad) { if (full) NB_LAUNCHB(true, true, false); else if (tab) NB_LAUNCHB(true, false, true); else NB_LAUNCHB(true, false, false); }
-            else { if (full) NB_LAUNCHB(false, true, false); else if (tab) NB_LAUNCHB(false, false, true); else NB_LAUNCHB(false, false, false); }
-        } else if (e->packed) {
-            if (grad) { if (full) NB_LAUNCH2(true, true, false); else if (tab) NB_LAUNCH2(true, false, true); else NB_LAUNCH2(true, false, false); }
-            else { if (full) NB_LAUNCH2(false, true, false); else if (tab) NB_LAUNCH2(false, false, true); else NB_LAUNCH2(false, false, false); }
-        } else {
-            if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
-            else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
-        }
+        const int n_ep = nb_eparts(e, B), n_blk = nb_blocks(e, B);
+        // with a gradient the batch goes in chunks of conformations whose partial forces fit the scratch (usually one chunk)
+        const int64_t chunk = grad ? nb_chunk(e, B) : B;
+        for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+            const int Bc = (int)std::min<int64_t>(chunk, B - b0);
+            const float* xc = x + b0 * sxb;
+            const float* wc = weights ? weights + 4 * b0 : nullptr;
+            double* ep = energies ? e_nb + b0 * n_ep : nullptr;
+            prof_begin(2, b0 == 0);
+            const unsigned blocks = (unsigned)(((long)Bc * e->n_pairs + NB_WARPS - 1) / NB_WARPS);
+#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(xc, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, Bc, fpart, wc, ep)
+#define NB_LAUNCH2(G, F, T) nb_kernel2<G, F, T><<<grid2, 32, T ? e->lut_n * sizeof(float2) : 0, stream>>>(xc, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, Bc, fpart, wc, ep, e->d_lrow, e->d_lpc, e->d_lut, e->lut_n)
+            const unsigned gy = (unsigned)std::min(e->n_pairs, 65535);
+            const dim3 grid2((unsigned)Bc, gy, (unsigned)((e->n_pairs + gy - 1) / gy));
+#define NB_LAUNCHB(G, F, T) nb_block_kernel<G, F, T><<<dim3((unsigned)Bc, (unsigned)std::min(S.items, 65535), (unsigned)((S.items + 65534) / 65535)), 32, e->blk_acc_smem + (T ? e->lut_n * sizeof(float2) : 0), stream>>>(xc, sxb, sxc, sxn, N, e->n_nbt, \
+                T ? e->d_tparl : (NB_WFORM && !F) ? e->d_tparw : e->d_tpar, S.d_items, e->d_pair_meta, e->d_masks, S.items, S.blocks, Bc, fpart, wc, ep, \
+                e->d_lut, e->lut_n, e->blk_acc_smem / (int)sizeof(float))
+            if (blocks_on) {
+                if (grad) { if (full) NB_LAUNCHB(true, true, false); else if (tab) NB_LAUNCHB(true, false, true); else NB_LAUNCHB(true, false, false); }
+                else { if (full) NB_LAUNCHB(false, true, false); else if (tab) NB_LAUNCHB(false, false, true); else NB_LAUNCHB(false, false, false); }
+            } else if (e->packed) {
+                if (grad) { if (full) NB_LAUNCH2(true, true, false); else if (tab) NB_LAUNCH2(true, false, true); else NB_LAUNCH2(true, false, false); }
+                else { if (full) NB_LAUNCH2(false, true, false); else if (tab) NB_LAUNCH2(false, false, true); else NB_LAUNCH2(false, false, false); }
+            } else {
+                if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
+                else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
+            }
 #undef NB_LAUNCHB
 #undef NB_LAUNCH2
 #undef NB_LAUNCH
-        LAUNCH_CHECK("the non-bonded pair kernel");
-        prof_end(2);
-        ++launches;
-        if (nb_first) {
-            if (int rc = bonded_checked()) return rc;
-            CK(cudaEventRecord(e->ev_join, e->side));
-        }
-        if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient (and sums its energy partials)
-        if (grad) {
-            prof_begin(3);
-            nb_reduce_kernel<<<dim3(e->n_nbt * (NB_T / 32), (unsigned)B), 32 * RED_PARTS, 0, stream>>>(fpart,
-                blocks_on ? S.d_red_off : e->d_red_off, blocks_on ? S.d_red_list : e->d_red_list, nb_eparts(e, B), nb_blocks(e, B), N,
-                grad, sgb, sgc, sgn, weights, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0,
-                e_bonded, e->n_tiles, e_nb, energies, term_mask);
-            LAUNCH_CHECK("nb_reduce_kernel");
-            prof_end(3);
+            LAUNCH_CHECK("the non-bonded pair kernel");
+            prof_end(2);
             ++launches;
-            energies_done = energies != nullptr;
+            if (b0 == 0) {
+                if (nb_first) {
+                    if (int rc = bonded_checked()) return rc;
+                    CK(cudaEventRecord(e->ev_join, e->side));
+                }
+                if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient (and sums its energy partials)
+            }
+            if (grad) {
+                prof_begin(3, b0 == 0);
+                nb_reduce_kernel<<<dim3(e->n_nbt * (NB_T / 32), (unsigned)Bc), 32 * RED_PARTS, 0, stream>>>(fpart,
+                    blocks_on ? S.d_red_off : e->d_red_off, blocks_on ? S.d_red_list : e->d_red_list, n_ep, n_blk, N,
+                    grad + b0 * sgb, sgb, sgc, sgn, wc, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0,
+                    e_bonded + b0 * e->n_tiles * 3, e->n_tiles, e_nb + b0 * n_ep, energies ? energies + 4 * b0 : nullptr, term_mask);
+                LAUNCH_CHECK("nb_reduce_kernel");
+                prof_end(3);
+                ++launches;
+                energies_done = energies != nullptr;
+            }
         }
     }
     if (energies && !energies_done) {
