@@ -76,6 +76,9 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #ifndef NB2_MINB
 #define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
 #endif
+#ifndef NB2_RCP_LUT
+#define NB2_RCP_LUT 0   // table form: 1/r^2 = (1/r)^2 on the FMA pipe (one MUFU per pair; with four resident warps the XU pipe was 50 % busy and MUFU issue the top stall: -1.3 %)
+#endif
 #ifndef NB2_MINB_LUT
 #define NB2_MINB_LUT 4   // the table form needs fewer registers: four resident warps per sub-partition (128 registers) - equal at MurD x 64, +2 % at 10 k atoms
 #endif
@@ -880,7 +883,7 @@ __device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival
 #endif
             float2 rinv2 = dup(0.f);
             float2 t2;
-#if NB_KO & 48
+#if (NB_KO & 48) || !NB2_RCP_LUT
             if (LUT) { rinv2 = __fmul2_rn(inv, inv); t2 = __fmul2_rn(Rij, rinv2); }
 #else
             if (LUT) { rinv2 = f2(rcp_fast(r2c.x), rcp_fast(r2c.y)); t2 = __fmul2_rn(Rij, rinv2); }
