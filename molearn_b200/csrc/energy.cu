@@ -770,6 +770,9 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
 #ifndef NB_REUSE_ORDER
 #define NB_REUSE_ORDER 1   // source order / operand choice that lets consecutive FFMA2s share operands (operand reuse cache)
 #endif
+#ifndef NB_PIPE_J
+#define NB_PIPE_J 0    // nb_kernel2: the j-group of the next rotation step is loaded before the shuffles of the current one
+#endif
 #ifndef NB_STEP_UNROLL
 #define NB_STEP_UNROLL 1   // rotation steps per trip of the pair loop
 #endif
@@ -915,7 +918,15 @@ __device__ __forceinline__ bool nb_micro2(const ival (&xi)[NB_NI][4], const ival
 #else
                 float2 s = __fmul2_rn(u, LUT ? rinv2 : __fmul2_rn(inv, inv));
 #endif
-#if NB_REUSE_ORDER
+#if NB_KO & 256
+                // knock-out: no accumulator operand (two register pairs read per operation instead of three)
+                Fi[a][0] = __fmul2_rn(s, dx); Fj[p][0] = __fmul2_rn(s, dx);
+                Fi[a][1] = __fmul2_rn(s, dy); Fj[p][1] = __fmul2_rn(s, dy);
+                Fi[a][2] = __fmul2_rn(s, dz); Fj[p][2] = __fmul2_rn(s, dz);
+#elif NB_KO & 512
+                // knock-out: the j-side accumulation only (half of the force operations)
+                Fj[p][0] = __ffma2_rn(s, dx, Fj[p][0]); Fj[p][1] = __ffma2_rn(s, dy, Fj[p][1]); Fj[p][2] = __ffma2_rn(s, dz, Fj[p][2]);
+#elif NB_REUSE_ORDER
                 // the i- and the j-side accumulation of a component share two of their three operands
                 facc(Fi[a][0], s, dx); Fj[p][0] = __ffma2_rn(s, dx, Fj[p][0]);
                 facc(Fi[a][1], s, dy); Fj[p][1] = __ffma2_rn(s, dy, Fj[p][1]);
@@ -1147,18 +1158,31 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     };
     int r = r_begin;
     constexpr int kStepUnroll = NB_STEP_UNROLL;
+    float4 cj[6];
+    cj[4] = cj[5] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_j = [&](int rr) {       // the lane's j-group of rotation step rr
+        const int g = (lane + rr) & 31;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cj[c] = s_j[c][g];
+        if (LUT) L.pc = s_pc[g];
+    };
+#if NB_PIPE_J
+    load_j(r);
+#endif
 #pragma unroll kStepUnroll
     for (; r < n_steps; ++r) {
         const int g = (lane + r) & 31;
-        float4 cj[6];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) cj[c] = s_j[c][g];
-        if (LUT) { L.pc = s_pc[g]; cj[4] = cj[5] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#if !NB_PIPE_J
+        load_j(r);
+#endif
         const bool mstep = (sbits >> r) & 1u;
         const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
         const bool close = mstep ? nb_micro2<GRAD, true, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L)
                                   : nb_micro2<GRAD, false, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L);
         if (close) fix_tile(cj, m16);
+#if NB_PIPE_J
+        load_j(r + 1);        // next step's shared-memory loads are issued before the shuffles of the rotation (their latencies overlap); the group past the last step is loaded and not used
+#endif
         rotate();
         // collapsed structures (an untrained decoder's output): when at least half of the lanes met a close pair in the
         // item's first step, the remaining steps are evaluated exactly, without the fast path (second loop)
@@ -1167,10 +1191,7 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
 #pragma unroll 1
     for (; r < n_steps; ++r) {
         const int g = (lane + r) & 31;
-        float4 cj[6];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) cj[c] = s_j[c][g];
-        if (LUT) { L.pc = s_pc[g]; cj[4] = cj[5] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        load_j(r);
         const bool mstep = (sbits >> r) & 1u;
         const uint32_t m16 = mstep ? sm16[g * 32 + lane] : 0xffffu;
         if (mstep) nb_micro2_exact<GRAD, true, FULL, LUT>(xi, hRi, sei, cj, m16, Fi, Fj, Sl, Sc, L);
@@ -1460,9 +1481,9 @@ nb_block_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, int N
 // grad[b, n] (+)= w_nb[b] * (sum of the partial forces of every tile pair in n's tile row / column),
 // summed in list order: reproducible.
 #ifndef RED_PARTS_N
-#define RED_PARTS_N 2
+#define RED_PARTS_N 4
 #endif
-constexpr int RED_PARTS = RED_PARTS_N;     // warps of a reduction CTA: each sums one contiguous quarter of an atom's block list
+constexpr int RED_PARTS = RED_PARTS_N;     // warps of a reduction CTA: each sums one contiguous share of the tile's block list
 __global__ void __launch_bounds__(32 * RED_PARTS)
 nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_off, const int* __restrict__ red_list,
                  int n_pairs /* energy partials per conformation */, int n_blocks /* partial-force blocks per conformation */,
@@ -1495,49 +1516,58 @@ nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_of
             energies[4 * b + tid] = (float)v;
         }
     }
-    // CTA = 32 consecutive atoms of one conformation; warp `part` sums its share of the tile's partial blocks,
-    // then part 0 adds the RED_PARTS sums in order: a fixed summation tree, reproducible, with 4x the loads in
-    // flight of a one-thread-per-atom loop (the kernel is latency-bound: 30 MB out of L2 for the headline batch)
-    __shared__ float s_part[RED_PARTS][3][32];
+    // CTA = one 128-atom tile of one conformation; a lane owns four consecutive atoms (16-byte loads of the partial
+    // blocks), warp `part` sums its contiguous share of the tile's block list, then part 0 adds the RED_PARTS sums in
+    // order: a fixed summation tree, reproducible.  30 MB out of L2 for the headline batch in 9 us + launch; the same
+    // time as one atom per lane and two warps per 32 atoms, with a quarter of the load instructions.
+    __shared__ float4 s_part[RED_PARTS][3][32];
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    const int n = blockIdx.x * 32 + lane;
-    const int T = (blockIdx.x * 32) / NB_T, l = (blockIdx.x * 32) % NB_T + lane;
+    const int T = blockIdx.x;
+    const int n = T * NB_T + 4 * lane;
     const float w = weights ? weights[4 * b + 3] : 1.f;
-    float* g = grad + (long)b * sgb + (long)n * sgn;
     if (skip_zero_weight && w == 0.f) {          // nb_kernel wrote no partials for this conformation
-        if (part == 0 && n < N && !accumulate) { g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
+        if (part == 0 && !accumulate) {
+            float* g = grad + (long)b * sgb + (long)n * sgn;
+            for (int a = 0; a < 4 && n + a < N; ++a, g += sgn) { g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
+        }
         return;
     }
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    const float* base = fpart + (long)b * n_blocks * (3 * NB_T) + l;
+    float4 sx = make_float4(0.f, 0.f, 0.f, 0.f), sy = sx, sz = sx;
+    const float4* base = reinterpret_cast<const float4*>(fpart + (long)b * n_blocks * (3 * NB_T)) + lane;
     const int k0 = red_off[T], k1 = red_off[T + 1];
     const int per = (k1 - k0 + RED_PARTS - 1) / RED_PARTS;
     const int ka = min(k1, k0 + part * per), kb = min(k1, ka + per);
+    auto add4 = [](float4& s, const float4& v) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; };
     int k = ka;
     for (; k + 4 <= kb; k += 4) {
-        float vx[4], vy[4], vz[4];
+        float4 vx[4], vy[4], vz[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int e = red_list[k + u];
-            const float* p = base + (long)e * (3 * NB_T);       // entry = block index (nb_kernel2: pair*2 + side)
-            vx[u] = p[0]; vy[u] = p[NB_T]; vz[u] = p[2 * NB_T];
+            const float4* p = base + (long)red_list[k + u] * (3 * NB_T / 4);       // entry = block index (nb_kernel2: pair*2 + side)
+            vx[u] = p[0]; vy[u] = p[NB_T / 4]; vz[u] = p[2 * NB_T / 4];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { sx += vx[u]; sy += vy[u]; sz += vz[u]; }
+        for (int u = 0; u < 4; ++u) { add4(sx, vx[u]); add4(sy, vy[u]); add4(sz, vz[u]); }
     }
     for (; k < kb; ++k) {
-        const int e = red_list[k];
-        const float* p = base + (long)e * (3 * NB_T);
-        sx += p[0]; sy += p[NB_T]; sz += p[2 * NB_T];
+        const float4* p = base + (long)red_list[k] * (3 * NB_T / 4);
+        add4(sx, p[0]); add4(sy, p[NB_T / 4]); add4(sz, p[2 * NB_T / 4]);
     }
     s_part[part][0][lane] = sx; s_part[part][1][lane] = sy; s_part[part][2][lane] = sz;
     __syncthreads();
-    if (part == 0 && n < N) {
+    if (part == 0) {
 #pragma unroll
-        for (int q = 1; q < RED_PARTS; ++q) { sx += s_part[q][0][lane]; sy += s_part[q][1][lane]; sz += s_part[q][2][lane]; }
-        if (accumulate) { g[0] = fmaf(w, sx, g[0]); g[sgc] = fmaf(w, sy, g[sgc]); g[2 * sgc] = fmaf(w, sz, g[2 * sgc]); }
-        else { g[0] = w * sx; g[sgc] = w * sy; g[2 * sgc] = w * sz; }
+        for (int q = 1; q < RED_PARTS; ++q) { add4(sx, s_part[q][0][lane]); add4(sy, s_part[q][1][lane]); add4(sz, s_part[q][2][lane]); }
+        const float fx[4] = {sx.x, sx.y, sx.z, sx.w}, fy[4] = {sy.x, sy.y, sy.z, sy.w}, fz[4] = {sz.x, sz.y, sz.z, sz.w};
+        float* g = grad + (long)b * sgb + (long)n * sgn;
+#pragma unroll
+        for (int a = 0; a < 4; ++a, g += sgn) {
+            if (n + a < N) {
+                if (accumulate) { g[0] = fmaf(w, fx[a], g[0]); g[sgc] = fmaf(w, fy[a], g[sgc]); g[2 * sgc] = fmaf(w, fz[a], g[2 * sgc]); }
+                else { g[0] = w * fx[a]; g[sgc] = w * fy[a]; g[2 * sgc] = w * fz[a]; }
+            }
+        }
     }
 }
 
@@ -2660,7 +2690,7 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
             }
             if (grad) {
                 prof_begin(3, b0 == 0);
-                nb_reduce_kernel<<<dim3(e->n_nbt * (NB_T / 32), (unsigned)Bc), 32 * RED_PARTS, 0, stream>>>(fpart,
+                nb_reduce_kernel<<<dim3(e->n_nbt, (unsigned)Bc), 32 * RED_PARTS, 0, stream>>>(fpart,
                     blocks_on ? S.d_red_off : e->d_red_off, blocks_on ? S.d_red_list : e->d_red_list, n_ep, n_blk, N,
                     grad + b0 * sgb, sgb, sgc, sgn, wc, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0,
                     e_bonded + b0 * e->n_tiles * 3, e->n_tiles, e_nb + b0 * n_ep, energies ? energies + 4 * b0 : nullptr, term_mask);
