@@ -56,9 +56,11 @@
 #ifndef BONDED_THREADS
 #define BONDED_THREADS 128
 #endif
-constexpr int BT = BONDED_THREADS;  // bonded: threads per CTA = atoms per tile
+constexpr int BT = BONDED_THREADS;  // bonded: threads per CTA (a multiple of 32, >= BTA)
+constexpr int BTA = 128;         // bonded: most atoms per tile (one gather thread per atom)
+static_assert(BT % 32 == 0 && BT >= BTA, "one gather thread per tile atom");
 constexpr int RI = 2;            // bonded: max work items per thread
-constexpr int SLOT_STRIDE = BT + 1;  // odd stride (in float4s): an atom's consecutive slots fall into different banks
+constexpr int SLOT_STRIDE = BTA + 1;  // odd stride (in float4s): an atom's consecutive slots fall into different banks
 constexpr int PF = 4;            // bonded: coordinate elements staged per thread (3*(own+halo) <= PF*BT)
 constexpr int NF = 4;            // torsion Fourier orders kept (ff14SB periods are 1..4)
 constexpr int NB_T = 128;        // non-bonded tile edge (atoms)
@@ -71,7 +73,7 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #define BONDED_CPC_MAX 32   // conformations per bonded CTA (the item records are read once per CTA)
 #endif
 #ifndef BONDED_MINB
-#define BONDED_MINB 5   // bonded CTAs per SM the register budget is sized for (5 x 128 threads x 96 registers)
+#define BONDED_MINB (640 / BONDED_THREADS)   // bonded CTAs per SM the register budget is sized for (20 warps x 96 registers)
 #endif
 #ifndef NB2_MINB
 #define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
@@ -2400,7 +2402,7 @@ Workspace layout(const mlp_energy* e, int64_t B, uint32_t term_mask, bool grad) 
 extern "C" {
 
 int mlp_bonded_plan(const mlp_topology* t, int tile_atoms, int64_t* n_items, int32_t* items, int64_t capacity, int64_t stats[4]) {
-    if (!t || !n_items || tile_atoms < 1 || tile_atoms > BT) { mlp_set_error("mlp_bonded_plan: bad argument"); return MLP_E_ARG; }
+    if (!t || !n_items || tile_atoms < 1 || tile_atoms > BTA) { mlp_set_error("mlp_bonded_plan: bad argument"); return MLP_E_ARG; }
     BondedPlan plan;
     int rc = plan_bonded(*t, tile_atoms, plan);
     if (rc == 1) { mlp_set_error("mlp_bonded_plan: topology too dense for this tile size"); return MLP_E_ARG; }
@@ -2445,8 +2447,8 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
     E->device = device; E->nb_mode = nb_mode; E->N = t->n_atoms;
     cudaDeviceGetAttribute(&E->sm_count, cudaDevAttrMultiProcessorCount, device);
     int rc = MLP_OK;
-    int tile = BT;
-    if (const char* env = std::getenv("MLP_BONDED_TILE")) tile = std::max(32, std::min(BT, std::atoi(env) & ~7));
+    int tile = BTA;
+    if (const char* env = std::getenv("MLP_BONDED_TILE")) tile = std::max(32, std::min(BTA, std::atoi(env) & ~7));
     while (true) {
         rc = pack_bonded(E, *t, tile);
         if (rc == 1 && tile > 32) { tile -= 32; for (void* p : E->allocs) cudaFree(p); E->allocs.clear(); continue; }

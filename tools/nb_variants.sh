@@ -17,6 +17,6 @@ else
   export NB_TIME_CASES=${NB_TIME_CASES:-murd64}
   for f in $(ls $d/defs_*.txt | sort -t_ -k2 -n); do
     k=${f##*_}; k=${k%.txt}
-    [ -f $d/lib_$k.so ] && MOLEARN_B200_LIB=$d/lib_$k.so python tools/nb_time.py "$(cat $f)" 2>&1 | tail -1
+    [ -f $d/lib_$k.so ] && MOLEARN_B200_LIB=$d/lib_$k.so python ${NB_TIME_SCRIPT:-tools/nb_time.py} "$(cat $f)" 2>&1 | tail -1
   done
 fi
