@@ -126,6 +126,13 @@ void mlp_topology_destroy(mlp_topology* t);
 int mlp_bonded_plan(const mlp_topology* t, int tile_atoms, int64_t* n_items, int32_t* items, int64_t capacity,
                     int64_t stats[4]);
 
+/* Host only: the Lennard-Jones classes the repulsive pair kernel's type-pair table is built from.  Atoms with the same
+ * (R, eps) share a class (numbered in order of first appearance); w2[a*n+b] = ((12 eps_ab)^(1/12) R_ab)^2 with the
+ * reference's combination rules R_ab = (R_a+R_b)/2, eps_ab = sqrt(eps_a eps_b) (utils.py:814-815), so that
+ * w2^6 / 12 = vdw_A[i,j] of utils.py:816 for any non-excluded pair of those classes.  atom_class [n_atoms] and w2
+ * [capacity >= n^2] may be NULL (call once with w2 = NULL to size it); *n_classes receives n. */
+int mlp_nb_pair_table(const mlp_topology* t, int32_t* atom_class, float* w2, int64_t capacity, int64_t* n_classes);
+
 /* Number of CUDA devices visible (0 if none / no driver).  Never fails. */
 int mlp_device_count(void);
 

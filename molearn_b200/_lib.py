@@ -25,6 +25,7 @@ SYMBOLS = {
     "mlp_topology_params14": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "mlp_topology_destroy": (None, [c_void_p]),
     "mlp_bonded_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mlp_nb_pair_table": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mlp_device_count": (c_int, []),
     "mlp_energy_create": (c_int, [c_void_p, c_int, c_uint32, POINTER(c_void_p)]),
     "mlp_energy_destroy": (None, [c_void_p]),

@@ -2140,6 +2140,34 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
     return MLP_OK;
 }
 
+// Lennard-Jones classes of a topology: atoms with the same (R, eps) in order of first appearance, and the squared pair
+// length w^2(a, b) = ((12 eps_ab)^(1/12) R_ab)^2 with R_ab = (R_a + R_b)/2, eps_ab = sqrt(eps_a eps_b) (utils.py:814-815),
+// evaluated in fp64 and rounded once.  (w/d)^12 / 12 is the reference's vdw_A / d^12.
+struct LjClasses {
+    std::vector<int> of;          // [N] class of each atom
+    std::vector<double> R, eps;   // per class
+    int n() const { return (int)R.size(); }
+    float w2(int a, int b) const {
+        const double w = std::pow(12.0 * std::sqrt(eps[a] * eps[b]), 1.0 / 12.0) * 0.5 * (R[a] + R[b]);
+        return (float)(w * w);
+    }
+};
+LjClasses lj_classes(const mlp_topology& T) {
+    LjClasses L;
+    std::map<std::pair<float, float>, int> cls;
+    L.of.resize(T.n_atoms);
+    for (int i = 0; i < T.n_atoms; ++i) {
+        const auto key = std::make_pair(T.vdw_R[i], T.vdw_e[i]);
+        auto it = cls.find(key);
+        if (it == cls.end()) {
+            it = cls.emplace(key, (int)cls.size()).first;
+            L.R.push_back(key.first); L.eps.push_back(key.second);
+        }
+        L.of[i] = it->second;
+    }
+    return L;
+}
+
 int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     const int N = T.n_atoms;
     const int nt = (N + NB_T - 1) / NB_T;
@@ -2158,26 +2186,14 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     // Lennard-Jones classes: atoms with the same (R, eps).  Up to NB_LUT_MAXC classes (plus a zero class for the
     // padding atoms) the repulsive kernel reads w_ij^2 = ((12 eps_ij)^(1/12) R_ij)^2 from a table in shared memory.
     {
-        std::map<std::pair<float, float>, int> cls;
-        std::vector<int> c_of(E->Npad, 0);
-        for (int i = 0; i < N; ++i) {
-            auto key = std::make_pair(T.vdw_R[i], T.vdw_e[i]);
-            auto it = cls.find(key);
-            if (it == cls.end()) it = cls.emplace(key, (int)cls.size()).first;
-            c_of[i] = it->second;
-        }
-        const int C = (int)cls.size() + 1;
-        for (int i = N; i < E->Npad; ++i) c_of[i] = C - 1;
+        const LjClasses LJ = lj_classes(T);
+        const int C = LJ.n() + 1;
+        std::vector<int> c_of(E->Npad, C - 1);
+        for (int i = 0; i < N; ++i) c_of[i] = LJ.of[i];
         E->lut_classes = C;
         E->lut_on = false;
         if (C <= NB_LUT_MAXC + 1) {
-            std::vector<double> R(C, 0.0), ep(C, 0.0);
-            for (auto& kv : cls) { R[kv.second] = kv.first.first; ep[kv.second] = kv.first.second; }
-            auto w2 = [&](int a, int b) {
-                if (a == C - 1 || b == C - 1) return 0.f;
-                const double w = std::pow(12.0 * std::sqrt(ep[a] * ep[b]), 1.0 / 12.0) * 0.5 * (R[a] + R[b]);
-                return (float)(w * w);
-            };
+            auto w2 = [&](int a, int b) { return (a == C - 1 || b == C - 1) ? 0.f : LJ.w2(a, b); };
             std::vector<float2> lut((size_t)C * C * C);
             for (int a = 0; a < C; ++a)
                 for (int b0 = 0; b0 < C; ++b0)
@@ -2423,6 +2439,19 @@ int mlp_bonded_plan(const mlp_topology* t, int tile_atoms, int64_t* n_items, int
         stats[0] = (int64_t)plan.tiles.size(); stats[1] = plan.max_cnt; stats[2] = plan.torsion_sines ? 1 : 0;
         stats[3] = 0;
         for (char c : plan.t_live) stats[3] += c ? 1 : 0;
+    }
+    return MLP_OK;
+}
+
+int mlp_nb_pair_table(const mlp_topology* t, int32_t* atom_class, float* w2, int64_t capacity, int64_t* n_classes) {
+    if (!t || !n_classes) { mlp_set_error("mlp_nb_pair_table: null argument"); return MLP_E_ARG; }
+    const LjClasses L = lj_classes(*t);
+    const int C = L.n();
+    *n_classes = C;
+    if (atom_class) for (int i = 0; i < t->n_atoms; ++i) atom_class[i] = L.of[i];
+    if (w2) {
+        if (capacity < (int64_t)C * C) { mlp_set_error("mlp_nb_pair_table: w2 holds fewer than n_classes^2 floats"); return MLP_E_ARG; }
+        for (int a = 0; a < C; ++a) for (int b = 0; b < C; ++b) w2[(size_t)a * C + b] = L.w2(a, b);
     }
     return MLP_OK;
 }

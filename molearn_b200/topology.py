@@ -97,6 +97,18 @@ class Topology:
         return items, dict(tiles=int(st[0]), max_contributions_per_atom=int(st[1]), torsion_sines=bool(st[2]),
                            live_torsions=int(st[3]))
 
+    def nb_pair_table(self):
+        """Lennard-Jones classes and the squared pair lengths of the repulsive pair kernel's type-pair table
+        (host-only; ``mlp_nb_pair_table``).  Returns ``(atom_class [N] int32, w2 [C, C] float32)`` with
+        ``w2[a, b]**6 / 12 == vdw_A[i, j]`` (utils.py:816) for non-excluded atoms i, j of classes a, b."""
+        L = _lib.lib()
+        n = ctypes.c_int64(0)
+        cls = np.zeros(self.n_atoms, np.int32)
+        _lib.check(L.mlp_nb_pair_table(self._h, _vp(cls), None, 0, ctypes.byref(n)))
+        w2 = np.zeros((n.value, n.value), np.float32)
+        _lib.check(L.mlp_nb_pair_table(self._h, None, _vp(w2), w2.size, ctypes.byref(n)))
+        return cls, w2
+
     def as_dict(self):
         """Arrays under the names the golden fixtures / oracle use."""
         return dict(bond_idxs=self.bond_idxs, angle_idxs=self.angle_idxs, torsion_idxs=self.torsion_idxs,

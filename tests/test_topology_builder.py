@@ -58,6 +58,27 @@ def test_scaled_14_parameters_bit_exact(case14, golden_topo, param_dir):
     assert np.array_equal(t.q1q2_14, g["q1q2_14"].astype(np.float32))
 
 
+def test_nb_pair_table_reproduces_the_reference_lj_matrix(case, golden_topo, param_dir):
+    """The type-pair table of the repulsive pair kernel (``mlp_nb_pair_table``: w^2 per pair of Lennard-Jones classes,
+    fp64 on the host, rounded once) against the reference's own dense ``vdw_A`` matrix (utils.py:813-816, sampled into
+    the golden files by oracle/make_golden.py): (w_ij^2)^6 / 12 = eps_ij R_ij^12 for every sampled non-excluded pair,
+    and atoms share a class exactly when they share (R, eps)."""
+    from molearn_b200 import Topology
+    g = golden_topo(case)
+    t = Topology(atominfo_from(g), param_dir=param_dir)
+    cls, w2 = t.nb_pair_table()
+    C = w2.shape[0]
+    assert cls.min() == 0 and cls.max() == C - 1 and np.array_equal(w2, w2.T)
+    keys = np.stack([g["atom_R"], g["atom_e"]], 1)
+    assert len(np.unique(keys, axis=0)) == C
+    for c in range(C):
+        assert len(np.unique(keys[cls == c], axis=0)) == 1          # one (R, eps) per class
+    nz = g["nb_A"] != 0                                              # excluded pairs are zero in the reference's matrix
+    i, j = g["nb_i"][nz], g["nb_j"][nz]
+    A = w2[cls[i], cls[j]].astype(np.float64) ** 6 / 12.0
+    assert np.max(np.abs(A / g["nb_A"][nz] - 1)) < 5e-6             # the reference builds A in fp32; w^2 is rounded once
+
+
 def test_builder_matches_python_oracle_on_edge_inputs(param_dir):
     """Ragged / unusual inputs the golden files do not hold: OXT, HIS variants, CHARMM names,
     hydrogens with fix_h, a single residue, an empty list."""
