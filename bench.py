@@ -940,7 +940,7 @@ def main():
             topo_bytes = len(top.bond_idxs) * 16 + len(top.angle_idxs) * 32 + len(top.torsion_idxs) * 64
             byts = 24 * N * BB + topo_bytes
             gbs = byts / (t_ms * 1e-3) / 1e9
-            nb_ncu = ncu.get("bonded", {})
+            nb_ncu = ncu.get("bonded_b4096", {})       # the capture of this configuration (tools/ncu_round2.sh)
             out["roofline_bonded"] = {"kernel": "bonded_kernel<grad>", "bound": "hbm", "batch": BB, "achieved": gbs,
                                       "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                                       "traffic": nb_ncu.get("dram_bytes"), "ncu": nb_ncu or None, "ncu_capture_commit": ncu.get("commit"),
