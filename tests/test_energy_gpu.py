@@ -548,6 +548,24 @@ def test_51k_atoms_coincident_atoms_semantics(dev, system_51k):
     assert np.isfinite(got[0]) and np.isnan(got[1]) and np.isfinite(got[2]) and np.isfinite(got[3])
 
 
+def test_51k_atoms_one_warp_per_tile_pair(dev, system_51k, monkeypatch):
+    """The config-5 system through nb_kernel2 (MLP_NB_BLOCKS=0; by default a system of this size uses the block items
+    for their smaller scratch): 81 405 tile pairs are more than one grid dimension holds, so the pair index is split
+    over blockIdx.y and blockIdx.z.  Same tolerance against the oracle, and the same numbers as the block items."""
+    from molearn_b200 import TorchProteinEnergy
+    from molearn_b200.data import tile_system
+    tpe_blk, topo, x = system_51k
+    monkeypatch.setenv("MLP_NB_BLOCKS", "0")
+    g = load_golden_murd_bbcb()
+    tinfo, _ = tile_system(g[0], g[1], 24, batch=1, noise=0.2, seed=9)
+    tpe = TorchProteinEnergy(None, tinfo, device=dev)
+    assert tpe._dev().info()["nb_tile_pairs"] > 65535
+    got, want, g1, wg = _check_51k(tpe, topo, x, dev, [TOL] * 4, "md-like, one warp per tile pair")
+    assert rel(g1, wg.sum(0)) < TOL
+    got2, _, g2, _ = _check_51k(tpe_blk, topo, x, dev, [TOL] * 4, "md-like, block items")
+    assert abs(got[3] - got2[3]) <= 1e-6 * abs(got2[3]) and rel(g1, g2) < 1e-6
+
+
 def test_block_item_schedule_matches_tile_pair_schedule(dev, monkeypatch):
     """The two schedules of the pair term - one warp per tile pair (nb_kernel2) and one warp per block of tile pairs
     (nb_block_kernel: rows kept in registers, column forces accumulated in shared memory, cp.async double buffering) -
