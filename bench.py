@@ -858,6 +858,12 @@ def main():
         return ms, acc
 
     ms_graph, _ = timed_graph(args.steps, 2 * n_slots)
+    # the same loop with the gradient left on the device (a consumer on the GPU, e.g. the decoder's backward pass):
+    # H2D of every batch and D2H of its energies only - half the PCIe / host-memory traffic
+    gstep_full = gstep
+    gstep = GraphedEnergyStep(tpe, hx, n_streams=len(gstep_full.streams), gradient_to_host=False)
+    ms_graph_dev, _ = timed_graph(args.steps, 2 * n_slots)
+    gstep = gstep_full
     # parity of the replayed step with the eager call on the same host batch (bit for bit)
     ge, gg = gstep.result(0)
     xe = hx[0].to(dev).permute(0, 2, 1).requires_grad_(True)
@@ -872,6 +878,9 @@ def main():
            "mode": "GraphedEnergyStep: H2D + energy_per_conformation + backward + D2H of energies and gradient captured once per pinned "
                    "host buffer through the public autograd path, one CUDA-graph replay per batch, " + f"{n_slots} pinned buffers over {len(gstep.streams)} streams (consecutive batches overlap on the GPU like the two_streams mode); the host reads every result",
            "graph_equals_eager": graph_equal,
+           "gradient_on_device": {"value": world * B * args.steps / (ms_graph_dev * 1e-3), "ms_per_step": ms_graph_dev / args.steps,
+                                  "h2d_bytes_per_step": per, "d2h_bytes_per_step": B * 16,
+                                  "mode": "same graph replay, dE/dx stays on the device (only the energies [B,4] are read back)"},
            "eager_pipelined": eager,
            "pipelined_energy_and_gradient_call": {"value": world * B * pipe_steps / (ms_dir * 1e-3), "ms_per_step": ms_dir / pipe_steps,
                                                   "mode": "same eager pipeline through TorchProteinEnergy.energy_and_gradient (no autograd graph)"},

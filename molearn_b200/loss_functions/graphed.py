@@ -25,7 +25,11 @@ from .torch_protein_energy import TorchProteinEnergy
 
 
 class GraphedEnergyStep:
-    def __init__(self, energy: TorchProteinEnergy, host_batches, nonbonded: bool = True, n_streams: int = 2):
+    def __init__(self, energy: TorchProteinEnergy, host_batches, nonbonded: bool = True, n_streams: int = 2,
+                 gradient_to_host: bool = True):
+        """``gradient_to_host=False`` keeps dE/dx on the device (``result`` then returns the device tensor): the case of
+        a consumer that lives on the GPU, e.g. a decoder's backward pass - only the energies [B,4] cross PCIe."""
+        self.gradient_to_host = gradient_to_host
         if not host_batches:
             raise ValueError("GraphedEnergyStep needs at least one pinned host buffer")
         self.energy = energy
@@ -39,7 +43,9 @@ class GraphedEnergyStep:
                 raise ValueError(f"host buffer {k} is not pinned (tensor.pin_memory()): the H2D copy could not be asynchronous")
             B = hx.shape[0]
             slot = {"hx": hx, "dx": torch.empty((B, energy.n_atoms, 3), device=dev),
-                    "he": torch.empty((B, 4)).pin_memory(), "hg": torch.empty((B, energy.n_atoms, 3)).pin_memory(),
+                    "he": torch.empty((B, 4)).pin_memory(),
+                    "hg": (torch.empty((B, energy.n_atoms, 3)).pin_memory() if gradient_to_host
+                           else torch.empty((B, energy.n_atoms, 3), device=dev)),
                     "stream": self.streams[k % len(self.streams)], "done": torch.cuda.Event(), "graph": None}
             self.slots.append(slot)
         torch.cuda.synchronize(dev)
@@ -61,7 +67,7 @@ class GraphedEnergyStep:
         e = self.energy.energy_per_conformation(x, nonbonded=nonbonded)
         (g,) = torch.autograd.grad(e.sum(), x)
         slot["he"].copy_(e.detach(), non_blocking=True)
-        slot["hg"].copy_(g.permute(0, 2, 1), non_blocking=True)
+        slot["hg"].copy_(g.permute(0, 2, 1), non_blocking=True)        # D2H, or a device copy into the slot's own buffer
 
     def submit(self, k: int):
         """Queue batch k (its pinned input buffer must be filled): one graph launch on the slot's stream."""
@@ -71,7 +77,8 @@ class GraphedEnergyStep:
             slot["done"].record()
 
     def result(self, k: int):
-        """(energies [B,4], dE/dx [B,N,3]) of the last ``submit(k)`` in pinned host memory; waits for that batch."""
+        """(energies [B,4], dE/dx [B,N,3]) of the last ``submit(k)``; waits for that batch.  Pinned host memory (the
+        gradient is a device tensor with ``gradient_to_host=False``)."""
         slot = self.slots[k]
         slot["done"].synchronize()
         return slot["he"], slot["hg"]
