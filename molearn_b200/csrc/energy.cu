@@ -72,6 +72,9 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #ifndef BONDED_CPC_MAX
 #define BONDED_CPC_MAX 32   // conformations per bonded CTA (the item records are read once per CTA)
 #endif
+#ifndef BONDED_DB
+#define BONDED_DB 0   // 1: bonded kernel double-buffered over conformations, one barrier per conformation instead of two (twice the shared memory; measured SLOWER: 0.270 vs 0.258 ms at B = 4096)
+#endif
 #ifndef BONDED_MINB
 #define BONDED_MINB (640 / BONDED_THREADS)   // bonded CTAs per SM the register budget is sized for (20 warps x 96 registers)
 #endif
@@ -350,9 +353,14 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
               int B, int conf_per_cta, uint32_t term_mask, int accumulate, int max_atoms, int max_cnt) {
     constexpr int STRIDE = SLOT_STRIDE;  // slot (atom a, k-th contribution) at k*STRIDE + a
     extern __shared__ float4 smem[];
-    float4* sc = smem;                 // [max_atoms] coordinates of own + halo atoms
-    float4* slots = smem + max_atoms;  // [max_cnt*STRIDE + 1] gradient slots; last = dump
-    __shared__ float s_e[3][BT];
+    // Double-buffered over conformations (BONDED_DB): conformation b's items write slots[b & 1] while the slower
+    // threads still gather conformation b-1 from the other half, and the coordinates of b+1 are staged into the other
+    // coordinate buffer - ONE barrier per conformation instead of two.
+    constexpr int NBUF = BONDED_DB ? 2 : 1;
+    const int slot_span = max_cnt * STRIDE + 1;
+    float4* sc0 = smem;                          // [NBUF][max_atoms] coordinates of own + halo atoms
+    float4* slots0 = smem + NBUF * max_atoms;    // [NBUF][max_cnt*STRIDE + 1] gradient slots; last = dump
+    __shared__ float s_e[NBUF][3][BT];
 
     const BTile t = tiles[blockIdx.x];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -380,7 +388,7 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
     const int my_cnt = (GRAD && tid < t.n_own) ? cnts[t.cnt_off + tid] : 0;
     const int wcnt = (__reduce_max_sync(0xffffffffu, my_cnt) + 3) & ~3;   // <= max_cnt (a multiple of 4)
     if (GRAD) {
-        for (int s = tid; s < max_cnt * STRIDE; s += BT) slots[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = tid; s < NBUF * slot_span; s += BT) slots0[s] = make_float4(0.f, 0.f, 0.f, 0.f);
         // ordered before the first slot write by the first __syncthreads of the conformation loop
     }
 
@@ -411,7 +419,6 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
             }
         }
     }
-    float* scf = reinterpret_cast<float*>(sc);
 
     const int b0 = blockIdx.y * conf_per_cta;
     const int b1 = min(B, b0 + conf_per_cta);
@@ -425,37 +432,17 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
     const int gofs = (t.a0 + tid) * sgn;
     const bool do_b = term_mask & MLP_TERM_BOND, do_a = term_mask & MLP_TERM_ANGLE, do_t = term_mask & MLP_TERM_TORSION;
 
-    if (b0 < b1) prefetch(xb);
-    for (int b = b0; b < b1; ++b, xb += sxb, gb += sgb) {
-        float wb = 1.f, wa = 1.f, wt = 1.f;
-        if (weights) { wb = weights[4 * b]; wa = weights[4 * b + 1]; wt = weights[4 * b + 2]; }
-        if (GRAD && weights && !e_part && (!do_b || wb == 0.f) && (!do_a || wa == 0.f) && (!do_t || wt == 0.f)) {
-            // every requested term of this conformation has zero upstream weight (CTA-uniform): nothing to add, or an
-            // exact zero to store - the coordinates are not even read, so a non-finite conformation cannot leak NaN * 0
-            if (!accumulate && tid < t.n_own) { float* g = gb + gofs; g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
-            if (b + 1 < b1) prefetch(xb + sxb);
-            continue;
-        }
-        // a term with zero upstream weight is dropped like a term the item does not carry (its degenerate-geometry
-        // NaN must not reach the gradient as NaN * 0); its energy is still counted
-        const uint32_t wdrop = weights ? ((wt == 0.f ? IT_T : 0u) | (wa == 0.f ? IT_A : 0u) | (wb == 0.f ? IT_B : 0u)) : 0u;
-        // stage coordinates (the previous iteration's term phase is over: everybody passed its second barrier)
+    auto stage = [&](float4* sc) {        // prefetched registers -> coordinate buffer
+        float* scf = reinterpret_cast<float*>(sc);
 #pragma unroll
         for (int q = 0; q < PF; ++q) if (sidx[q] >= 0) scf[sidx[q]] = pf[q];
-        __syncthreads();
-        if (b + 1 < b1) prefetch(xb + sxb);
-
-        float eb = 0.f, ea = 0.f, et = 0.f;
-#pragma unroll
-        for (int r = 0; r < RI; ++r)
-            if (ai[r]) item_term<GRAD, SG>(sc, slots, ri[r], rs[r], ri[r].flags & ~wdrop, wb, wa, wt, eb, ea, et);
-        if (e_part) { s_e[0][tid] = eb; s_e[1][tid] = ea; s_e[2][tid] = et; }
-        __syncthreads();
+    };
+    auto energy_and_gather = [&](int b, const float4* slots, const float (*se)[BT], float* gb) {
         if (e_part && warp < 3) {
             // warp w sums term w over the CTA in a fixed order (reproducible); the other warps go on
             float s = 0.f;
 #pragma unroll
-            for (int k = 0; k < BT / 32; ++k) s += s_e[warp][lane + 32 * k];
+            for (int k = 0; k < BT / 32; ++k) s += se[warp][lane + 32 * k];
             s = warp_sum(s);
             if (lane == 0) e_part[((long)b * gridDim.x + blockIdx.x) * 3 + warp] = s;
         }
@@ -474,9 +461,75 @@ bonded_kernel(const BTile* __restrict__ tiles, const int* __restrict__ halo, con
                 else { g[0] = gx; g[sgc] = gy; g[2 * sgc] = gz; }
             }
         }
+    };
+    // every requested term of a conformation has zero upstream weight (CTA-uniform): nothing to add, or an exact zero to
+    // store - its coordinates never enter any arithmetic, so a non-finite conformation cannot leak NaN * 0
+    auto all_zero = [&](float wb, float wa, float wt) {
+        return GRAD && weights && !e_part && (!do_b || wb == 0.f) && (!do_a || wa == 0.f) && (!do_t || wt == 0.f);
+    };
+#if BONDED_DB
+    if (b0 < b1) {
+        prefetch(xb);
+        stage(sc0);
+        if (b0 + 1 < b1) prefetch(xb + sxb);
+    }
+    __syncthreads();
+    for (int b = b0; b < b1; ++b, xb += sxb, gb += sgb) {
+        const int cur = (b - b0) & 1;
+        float4* sc = sc0 + cur * max_atoms;
+        float4* slots = slots0 + cur * slot_span;
+        float wb = 1.f, wa = 1.f, wt = 1.f;
+        if (weights) { wb = weights[4 * b]; wa = weights[4 * b + 1]; wt = weights[4 * b + 2]; }
+        const bool skip = all_zero(wb, wa, wt);
+        // a term with zero upstream weight is dropped like a term the item does not carry (its degenerate-geometry
+        // NaN must not reach the gradient as NaN * 0); its energy is still counted
+        const uint32_t wdrop = weights ? ((wt == 0.f ? IT_T : 0u) | (wa == 0.f ? IT_A : 0u) | (wb == 0.f ? IT_B : 0u)) : 0u;
+        if (!skip) {
+            float eb = 0.f, ea = 0.f, et = 0.f;
+#pragma unroll
+            for (int r = 0; r < RI; ++r)
+                if (ai[r]) item_term<GRAD, SG>(sc, slots, ri[r], rs[r], ri[r].flags & ~wdrop, wb, wa, wt, eb, ea, et);
+            if (e_part) { s_e[cur][0][tid] = eb; s_e[cur][1][tid] = ea; s_e[cur][2][tid] = et; }
+        }
+        // next conformation: registers -> the other coordinate buffer (its last readers, the items of b-1, are behind the
+        // previous barrier), then the loads of the one after it
+        if (b + 1 < b1) {
+            stage(sc0 + (cur ^ 1) * max_atoms);
+            if (b + 2 < b1) prefetch(xb + 2 * sxb);
+        }
+        __syncthreads();
+        // slots[cur] / s_e[cur] are complete; they are written again two conformations later, behind the next barrier
+        if (!skip) energy_and_gather(b, slots, s_e[cur], gb);
+        else if (!accumulate && tid < t.n_own) { float* g = gb + gofs; g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
+    }
+#else
+    float4* sc = sc0;
+    float4* slots = slots0;
+    if (b0 < b1) prefetch(xb);
+    for (int b = b0; b < b1; ++b, xb += sxb, gb += sgb) {
+        float wb = 1.f, wa = 1.f, wt = 1.f;
+        if (weights) { wb = weights[4 * b]; wa = weights[4 * b + 1]; wt = weights[4 * b + 2]; }
+        if (all_zero(wb, wa, wt)) {
+            if (!accumulate && tid < t.n_own) { float* g = gb + gofs; g[0] = 0.f; g[sgc] = 0.f; g[2 * sgc] = 0.f; }
+            if (b + 1 < b1) prefetch(xb + sxb);
+            continue;
+        }
+        const uint32_t wdrop = weights ? ((wt == 0.f ? IT_T : 0u) | (wa == 0.f ? IT_A : 0u) | (wb == 0.f ? IT_B : 0u)) : 0u;
+        // stage coordinates (the previous iteration's term phase is over: everybody passed its second barrier)
+        stage(sc);
+        __syncthreads();
+        if (b + 1 < b1) prefetch(xb + sxb);
+        float eb = 0.f, ea = 0.f, et = 0.f;
+#pragma unroll
+        for (int r = 0; r < RI; ++r)
+            if (ai[r]) item_term<GRAD, SG>(sc, slots, ri[r], rs[r], ri[r].flags & ~wdrop, wb, wa, wt, eb, ea, et);
+        if (e_part) { s_e[0][0][tid] = eb; s_e[0][1][tid] = ea; s_e[0][2][tid] = et; }
+        __syncthreads();
+        energy_and_gather(b, slots, s_e[0], gb);
         // the next iteration's staging only touches sc (term phase done); its slot writes happen after the
         // next barrier, i.e. after every gather above.
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2126,7 +2179,7 @@ int pack_bonded(mlp_energy* E, const mlp_topology& T, int tile_atoms) {
         max_atoms = std::max(max_atoms, n_at);
         tiles.push_back(bt);
     }
-    const size_t smem = ((size_t)max_atoms + (size_t)max_cnt * stride + 1) * sizeof(float4);
+    const size_t smem = (BONDED_DB ? 2 : 1) * ((size_t)max_atoms + (size_t)max_cnt * stride + 1) * sizeof(float4);   // both halves of the double buffer
     if (smem > 200 * 1024) { mlp_set_error("pack_bonded: too many gradient contributions per atom for the shared-memory slot table"); return MLP_E_ARG; }
     E->n_tiles = (int)tiles.size(); E->tile_atoms = tile_atoms; E->max_cnt = max_cnt;
     E->max_atoms = max_atoms; E->bonded_smem = smem; E->n_items = (long)n_items_real;
