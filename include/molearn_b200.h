@@ -149,9 +149,10 @@ void mlp_energy_destroy(mlp_energy* e);
  * The bulk is the pair term's partial forces: 3 KB per 128 x 128 tile pair and conformation (0.5 MB per MurD
  * conformation, 11 MB at 10 715 atoms).  It is bounded: a batch is evaluated in chunks of conformations whose
  * partial forces fit 384 MB (MLP_NB_WS_MB at create time; each chunk is one pair launch + one reduction), and a
- * system whose single conformation would need more than 64 MB (beyond ~26 k atoms) switches to block work items
- * that need about a fifth (49 MB per conformation at 51 432 atoms, 10 % slower).  Energy-only calls need 8 bytes
- * per tile pair and conformation. */
+ * system whose single conformation would need more than 64 MB (beyond ~26 k atoms) is evaluated band by band
+ * through the rows of its tile-pair triangle (<= 64 MB per conformation and launch: four bands at 51 432 atoms;
+ * MLP_NB_BANDS=0 selects block work items instead: 49 MB per conformation, 2 % slower).  Energy-only calls need
+ * 8 bytes per tile pair and conformation. */
 int64_t mlp_energy_workspace_bytes(const mlp_energy* e, int64_t B, uint32_t term_mask, int want_grad);
 
 /* Packing facts, for benchmarks and tests: info[0..7] = bonded tiles, atoms per bonded tile, max

@@ -81,6 +81,9 @@ constexpr int NB_WARPS = NB_WARPS_PER_CTA;  // warps per CTA, one work item each
 #ifndef NB2_MINB
 #define NB2_MINB 3   // packed kernel: resident warps per SM sub-partition the register budget is sized for
 #endif
+#ifndef NB_BLK_MEM_MB
+#define NB_BLK_MEM_MB 64   // most partial forces of one conformation in one pair launch; larger systems run band by band through their tile-pair rows
+#endif
 #ifndef NB2_RCP_LUT
 #define NB2_RCP_LUT 0   // table form: 1/r^2 = (1/r)^2 on the FMA pipe (one MUFU per pair; with four resident warps the XU pipe was 50 % busy and MUFU issue the top stall: -1.3 %)
 #endif
@@ -150,6 +153,13 @@ struct mlp_energy {
     uint32_t* d_lrow = nullptr;    // [Npad] byte offset of the atom's table row
     uint2* d_lpc = nullptr;        // [Npad/4] byte offsets, within a row, of the group's two j-atom pairs
     float2* d_lut = nullptr;       // [c][c][c] (w^2(ci, cj0), w^2(ci, cj1))
+    // row bands of the tile-pair list: when one conformation's partial forces exceed NB_BLK_MEM_MB the pair term runs
+    // band by band (rows [I_k, I_k+1) of the tile-pair triangle: pair launch, then a reduction that adds to the gradient)
+    struct PairBand { int begin = 0, count = 0; int* d_red_off = nullptr; int* d_red_list = nullptr; };
+    std::vector<PairBand> bands;
+    int4* d_pairs_b = nullptr;     // the pair list ordered band by band (longest first inside a band)
+    int band_max = 0;              // most pairs in a band
+    int band_mode = -1;            // MLP_NB_BANDS: -1 auto, 0 never (block items instead)
     int* d_red_off = nullptr;      // [n_nbt+1] per tile: range in d_red_list
     int* d_red_list = nullptr;     // entries pair*2 + side (0: the tile is the pair's I, 1: its J)
     // block-item schedules of the pair term (nb_block_kernel): used when there is much more work than warp slots;
@@ -1084,7 +1094,8 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
            const uint32_t* __restrict__ masks, const uint32_t* __restrict__ stepbits, int n_pairs, int B,
            float* __restrict__ fpart, const float* __restrict__ weights, double* __restrict__ e_part,
            const uint32_t* __restrict__ lrow /* [Npad] */, const uint2* __restrict__ lpc /* [Npad/4] */,
-           const float2* __restrict__ lut, int lut_n) {
+           const float2* __restrict__ lut, int lut_n, int e_stride /* energy partials per conformation */,
+           int e_off /* of this launch's first pair (row bands) */) {
     constexpr int NC = LUT ? 4 : 6;                // LUT: (x, y, z, q) only; the pair codes replace the two LJ parameters
     __shared__ float4 s_j[NC][32];                 // component c of the 128 j-atoms: s_j[c][g] = atoms 4g..4g+3
     __shared__ uint2 s_pc[LUT ? 32 : 1];           // LUT: table offsets of the two j-atom pairs of group g
@@ -1265,7 +1276,7 @@ nb_kernel2(const float* __restrict__ x, long sxb, long sxc, long sxn, const floa
     }
     if (e_part) {
         double e = (double)warp_sum(Sl.x + Sl.y) * (1.0 / 12.0) + (double)warp_sum(Sc.x + Sc.y);
-        if (lane == 0) e_part[item] = e;
+        if (lane == 0) e_part[(long)b * e_stride + e_off + p] = e;
     }
 }
 
@@ -1591,6 +1602,7 @@ nb_reduce_kernel(const float* __restrict__ fpart, const int* __restrict__ red_of
     float4 sx = make_float4(0.f, 0.f, 0.f, 0.f), sy = sx, sz = sx;
     const float4* base = reinterpret_cast<const float4*>(fpart + (long)b * n_blocks * (3 * NB_T)) + lane;
     const int k0 = red_off[T], k1 = red_off[T + 1];
+    if (k0 == k1 && accumulate) return;          // a row band that does not touch this tile (CTA-uniform)
     const int per = (k1 - k0 + RED_PARTS - 1) / RED_PARTS;
     const int ka = min(k1, k0 + part * per), kb = min(k1, ka + per);
     auto add4 = [](float4& s, const float4& v) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; };
@@ -2334,6 +2346,39 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
         red_list.insert(red_list.end(), lists[t].begin(), lists[t].end());
         red_off[t + 1] = (int)red_list.size();
     }
+    // ---- row bands (large systems): at most NB_BLK_MEM_MB of partial forces per conformation and launch ----
+    E->bands.clear(); E->band_max = 0;
+    if ((size_t)E->n_pairs * 6 * NB_T * sizeof(float) > ((size_t)NB_BLK_MEM_MB << 20)) {
+        const size_t cap = ((size_t)NB_BLK_MEM_MB << 20) / (6 * NB_T * sizeof(float));
+        std::vector<int4> pairs_b;
+        int I0 = 0;
+        while (I0 < nt) {
+            size_t cnt = 0;
+            int I1 = I0;
+            while (I1 < nt && (I1 == I0 || cnt + (size_t)(nt - I1 - 1 + NB_DIAG_SPLIT) <= cap)) { cnt += (size_t)(nt - I1 - 1 + NB_DIAG_SPLIT); ++I1; }
+            mlp_energy::PairBand bd;
+            bd.begin = (int)pairs_b.size();
+            for (const std::vector<int4>* src : {&band, &clean, &diag})
+                for (const int4& q4 : *src) if (q4.x >= I0 && q4.x < I1) pairs_b.push_back(q4);
+            bd.count = (int)pairs_b.size() - bd.begin;
+            std::vector<std::vector<int>> bl(nt);
+            for (int p = 0; p < bd.count; ++p) {
+                bl[pairs_b[bd.begin + p].x].push_back(2 * p);
+                bl[pairs_b[bd.begin + p].y].push_back(2 * p + 1);
+            }
+            std::vector<int> boff(nt + 1, 0), blist;
+            for (int t = 0; t < nt; ++t) { blist.insert(blist.end(), bl[t].begin(), bl[t].end()); boff[t + 1] = (int)blist.size(); }
+            if (blist.empty()) blist.push_back(0);
+            int rcb;
+            if ((rcb = upload(E, &bd.d_red_off, boff))) return rcb;
+            if ((rcb = upload(E, &bd.d_red_list, blist))) return rcb;
+            E->band_max = std::max(E->band_max, bd.count);
+            E->bands.push_back(bd);
+            I0 = I1;
+        }
+        int rcb;
+        if ((rcb = upload(E, &E->d_pairs_b, pairs_b))) return rcb;
+    }
     // ---- block-item schedule (nb_block_kernel) ----
     std::vector<float> tpar((size_t)nt * 3 * NB_T), tparw((size_t)nt * 3 * NB_T);
     for (int n = 0; n < E->Npad; ++n) {
@@ -2432,6 +2477,7 @@ int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pai
         return NB_BLK_LEVELS - 1;
     }
     if ((size_t)e->n_pairs * 6 * NB_T * sizeof(float) <= ((size_t)NB_BLK_MEM_MB << 20)) return -1;
+    if (e->band_mode != 0 && !e->bands.empty()) return -1;       // the tile-pair kernel, band by band
     // memory-bound regime: the biggest blocks that still leave every resident warp slot NB_BLK_MIN_ITEMS items, at least 4 rows
     const bool tab = e->lut_on && e->nb_mode != MLP_NB_FULL;
     const double per_slot = (double)e->n_nbt * (e->n_nbt + 1) / 2 * (double)B / ((double)e->sm_count * 4 * (tab ? NB2_MINB_LUT : NB2_MINB));
@@ -2441,7 +2487,11 @@ int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pai
     return best;
 }
 // partial-force blocks (3 x 128 floats) and energy partials per conformation under the schedule in use
-int nb_blocks(const mlp_energy* e, int64_t B) { const int lv = block_level(e, B); return lv >= 0 ? e->blk[lv].blocks : 2 * e->n_pairs; }
+bool banded(const mlp_energy* e, int64_t B) { return e->packed && e->band_mode != 0 && !e->bands.empty() && block_level(e, B) < 0; }
+int nb_blocks(const mlp_energy* e, int64_t B) {
+    const int lv = block_level(e, B);
+    return lv >= 0 ? e->blk[lv].blocks : banded(e, B) ? 2 * e->band_max : 2 * e->n_pairs;
+}
 int nb_eparts(const mlp_energy* e, int64_t B) { const int lv = block_level(e, B); return lv >= 0 ? e->blk[lv].items : e->n_pairs; }
 
 // conformations per pair launch: the partial forces of a chunk fit the scratch cap (at least one conformation)
@@ -2543,6 +2593,7 @@ int mlp_energy_create(const mlp_topology* t, int device, uint32_t nb_mode, mlp_e
         if (const char* env = std::getenv("MLP_NB_FIRST")) E->nb_first = std::atoi(env) != 0;
         E->ws_cap_mb = NB_WS_CAP_MB;
         if (const char* env = std::getenv("MLP_NB_WS_MB")) E->ws_cap_mb = std::max(1, std::atoi(env));
+        if (const char* env = std::getenv("MLP_NB_BANDS")) E->band_mode = std::atoi(env);
         if (const char* env = std::getenv("MLP_NB_BLOCKS")) E->blk_mode = std::max(0, std::atoi(env));   // 0: never, 2/4/8: always that block height
         if (const char* env = std::getenv("MLP_NB_PACKED")) E->packed = std::atoi(env) != 0;
         if (const char* env = std::getenv("MLP_NB_LUT")) E->lut_on = E->lut_on && std::atoi(env) != 0;
@@ -2733,55 +2784,67 @@ int mlp_energy_eval(mlp_energy* e, const float* x, int64_t B, int64_t sxb, int64
         const mlp_energy::BlockSchedule& S = e->blk[blocks_on ? lv : 0];
         const bool tab = !full && e->lut_on;
         const int n_ep = nb_eparts(e, B), n_blk = nb_blocks(e, B);
-        // with a gradient the batch goes in chunks of conformations whose partial forces fit the scratch (usually one chunk)
+        // with a gradient the batch goes in chunks of conformations whose partial forces fit the scratch (usually one chunk),
+        // and a large system band by band through its tile-pair rows
         const int64_t chunk = grad ? nb_chunk(e, B) : B;
+        const bool bands_on = grad && !blocks_on && banded(e, B);
+        const int n_bands = bands_on ? (int)e->bands.size() : 1;
         for (int64_t b0 = 0; b0 < B; b0 += chunk) {
             const int Bc = (int)std::min<int64_t>(chunk, B - b0);
             const float* xc = x + b0 * sxb;
             const float* wc = weights ? weights + 4 * b0 : nullptr;
             double* ep = energies ? e_nb + b0 * n_ep : nullptr;
-            prof_begin(2, b0 == 0);
-            const unsigned blocks = (unsigned)(((long)Bc * e->n_pairs + NB_WARPS - 1) / NB_WARPS);
-#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(xc, sxb, sxc, sxn, e->d_q, N, e->d_par, e->d_pairs, e->d_masks, e->n_pairs, Bc, fpart, wc, ep)
-#define NB_LAUNCH2(G, F, T) nb_kernel2<G, F, T><<<grid2, 32, T ? e->lut_n * sizeof(float2) : 0, stream>>>(xc, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, e->d_pairs, e->d_masks, e->d_stepbits, e->n_pairs, Bc, fpart, wc, ep, e->d_lrow, e->d_lpc, e->d_lut, e->lut_n)
-            const unsigned gy = (unsigned)std::min(e->n_pairs, 65535);
-            const dim3 grid2((unsigned)Bc, gy, (unsigned)((e->n_pairs + gy - 1) / gy));
+            for (int kb = 0; kb < n_bands; ++kb) {
+                const int4* plist = bands_on ? e->d_pairs_b + e->bands[kb].begin : e->d_pairs;
+                const int np = bands_on ? e->bands[kb].count : e->n_pairs;
+                const int e_off = bands_on ? e->bands[kb].begin : 0;
+                const bool first = b0 == 0 && kb == 0, last_band = kb == n_bands - 1;
+                prof_begin(2, first);
+                const unsigned blocks = (unsigned)(((long)Bc * np + NB_WARPS - 1) / NB_WARPS);
+#define NB_LAUNCH(G, F) nb_kernel<G, F><<<blocks, NB_WARPS * 32, 0, stream>>>(xc, sxb, sxc, sxn, e->d_q, N, e->d_par, plist, e->d_masks, np, Bc, fpart, wc, ep)
+#define NB_LAUNCH2(G, F, T) nb_kernel2<G, F, T><<<grid2, 32, T ? e->lut_n * sizeof(float2) : 0, stream>>>(xc, sxb, sxc, sxn, e->d_q, N, (NB_WFORM && !F) ? e->d_parw : e->d_par, plist, e->d_masks, e->d_stepbits, np, Bc, fpart, wc, ep, e->d_lrow, e->d_lpc, e->d_lut, e->lut_n, n_ep, e_off)
+                const unsigned gy = (unsigned)std::min(np, 65535);
+                const dim3 grid2((unsigned)Bc, gy, (unsigned)((np + gy - 1) / gy));
 #define NB_LAUNCHB(G, F, T) nb_block_kernel<G, F, T><<<dim3((unsigned)Bc, (unsigned)std::min(S.items, 65535), (unsigned)((S.items + 65534) / 65535)), 32, e->blk_acc_smem + (T ? e->lut_n * sizeof(float2) : 0), stream>>>(xc, sxb, sxc, sxn, N, e->n_nbt, \
-                T ? e->d_tparl : (NB_WFORM && !F) ? e->d_tparw : e->d_tpar, S.d_items, e->d_pair_meta, e->d_masks, S.items, S.blocks, Bc, fpart, wc, ep, \
-                e->d_lut, e->lut_n, e->blk_acc_smem / (int)sizeof(float))
-            if (blocks_on) {
-                if (grad) { if (full) NB_LAUNCHB(true, true, false); else if (tab) NB_LAUNCHB(true, false, true); else NB_LAUNCHB(true, false, false); }
-                else { if (full) NB_LAUNCHB(false, true, false); else if (tab) NB_LAUNCHB(false, false, true); else NB_LAUNCHB(false, false, false); }
-            } else if (e->packed) {
-                if (grad) { if (full) NB_LAUNCH2(true, true, false); else if (tab) NB_LAUNCH2(true, false, true); else NB_LAUNCH2(true, false, false); }
-                else { if (full) NB_LAUNCH2(false, true, false); else if (tab) NB_LAUNCH2(false, false, true); else NB_LAUNCH2(false, false, false); }
-            } else {
-                if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
-                else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
-            }
+                    T ? e->d_tparl : (NB_WFORM && !F) ? e->d_tparw : e->d_tpar, S.d_items, e->d_pair_meta, e->d_masks, S.items, S.blocks, Bc, fpart, wc, ep, \
+                    e->d_lut, e->lut_n, e->blk_acc_smem / (int)sizeof(float))
+                if (blocks_on) {
+                    if (grad) { if (full) NB_LAUNCHB(true, true, false); else if (tab) NB_LAUNCHB(true, false, true); else NB_LAUNCHB(true, false, false); }
+                    else { if (full) NB_LAUNCHB(false, true, false); else if (tab) NB_LAUNCHB(false, false, true); else NB_LAUNCHB(false, false, false); }
+                } else if (e->packed) {
+                    if (grad) { if (full) NB_LAUNCH2(true, true, false); else if (tab) NB_LAUNCH2(true, false, true); else NB_LAUNCH2(true, false, false); }
+                    else { if (full) NB_LAUNCH2(false, true, false); else if (tab) NB_LAUNCH2(false, false, true); else NB_LAUNCH2(false, false, false); }
+                } else {
+                    if (grad) { if (full) NB_LAUNCH(true, true); else NB_LAUNCH(true, false); }
+                    else { if (full) NB_LAUNCH(false, true); else NB_LAUNCH(false, false); }
+                }
 #undef NB_LAUNCHB
 #undef NB_LAUNCH2
 #undef NB_LAUNCH
-            LAUNCH_CHECK("the non-bonded pair kernel");
-            prof_end(2);
-            ++launches;
-            if (b0 == 0) {
-                if (nb_first) {
-                    if (int rc = bonded_checked()) return rc;
-                    CK(cudaEventRecord(e->ev_join, e->side));
-                }
-                if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient (and sums its energy partials)
-            }
-            if (grad) {
-                prof_begin(3, b0 == 0);
-                nb_reduce_kernel<<<dim3(e->n_nbt, (unsigned)Bc), 32 * RED_PARTS, 0, stream>>>(fpart,
-                    blocks_on ? S.d_red_off : e->d_red_off, blocks_on ? S.d_red_list : e->d_red_list, n_ep, n_blk, N,
-                    grad + b0 * sgb, sgb, sgc, sgn, wc, (accumulate || bonded) ? 1 : 0, (weights && !energies) ? 1 : 0,
-                    e_bonded + b0 * e->n_tiles * 3, e->n_tiles, e_nb + b0 * n_ep, energies ? energies + 4 * b0 : nullptr, term_mask);
-                LAUNCH_CHECK("nb_reduce_kernel");
-                prof_end(3);
+                LAUNCH_CHECK("the non-bonded pair kernel");
+                prof_end(2);
                 ++launches;
-                energies_done = energies != nullptr;
+                if (first) {
+                    if (nb_first) {
+                        if (int rc = bonded_checked()) return rc;
+                        CK(cudaEventRecord(e->ev_join, e->side));
+                    }
+                    if (fork) CK(cudaStreamWaitEvent(stream, e->ev_join, 0));   // the reduction adds to the bonded gradient (and sums its energy partials)
+                }
+                if (grad) {
+                    // a band's reduction adds to what the bands before it stored; the last one also sums the conformation's
+                    // energy partials (all pair launches of the chunk are behind it in stream order)
+                    prof_begin(3, first);
+                    nb_reduce_kernel<<<dim3(e->n_nbt, (unsigned)Bc), 32 * RED_PARTS, 0, stream>>>(fpart,
+                        bands_on ? e->bands[kb].d_red_off : blocks_on ? S.d_red_off : e->d_red_off,
+                        bands_on ? e->bands[kb].d_red_list : blocks_on ? S.d_red_list : e->d_red_list, n_ep, bands_on ? 2 * np : n_blk, N,
+                        grad + b0 * sgb, sgb, sgc, sgn, wc, (accumulate || bonded || kb > 0) ? 1 : 0, (weights && !energies) ? 1 : 0,
+                        e_bonded + b0 * e->n_tiles * 3, e->n_tiles, e_nb + b0 * n_ep, (energies && last_band) ? energies + 4 * b0 : nullptr, term_mask);
+                    LAUNCH_CHECK("nb_reduce_kernel");
+                    prof_end(3);
+                    ++launches;
+                    energies_done = energies != nullptr;
+                }
             }
         }
     }

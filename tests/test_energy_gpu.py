@@ -548,21 +548,30 @@ def test_51k_atoms_coincident_atoms_semantics(dev, system_51k):
     assert np.isfinite(got[0]) and np.isnan(got[1]) and np.isfinite(got[2]) and np.isfinite(got[3])
 
 
-def test_51k_atoms_one_warp_per_tile_pair(dev, system_51k, monkeypatch):
-    """The config-5 system through nb_kernel2 (MLP_NB_BLOCKS=0; by default a system of this size uses the block items
-    for their smaller scratch): 81 405 tile pairs are more than one grid dimension holds, so the pair index is split
-    over blockIdx.y and blockIdx.z.  Same tolerance against the oracle, and the same numbers as the block items."""
-    from molearn_b200 import TorchProteinEnergy
+@pytest.mark.parametrize("schedule", ["whole list", "block items"])
+def test_51k_atoms_other_pair_schedules(dev, system_51k, monkeypatch, schedule):
+    """The config-5 system runs the tile-pair kernel band by band through its tile rows (four launches of <= 64 MB of
+    partial forces per conformation).  Two other schedules must give the same numbers: the whole tile-pair list in one
+    launch (MLP_NB_BANDS=0 MLP_NB_BLOCKS=0: 81 405 tile pairs are more than one grid dimension holds, the pair index
+    spans blockIdx.y and blockIdx.z) and the block work items (MLP_NB_BANDS=0).  Each against the oracle at 1e-5 and
+    against the default at 1e-6."""
+    from molearn_b200 import TorchProteinEnergy, _lib
     from molearn_b200.data import tile_system
-    tpe_blk, topo, x = system_51k
-    monkeypatch.setenv("MLP_NB_BLOCKS", "0")
+    tpe_def, topo, x = system_51k
+    L = _lib.lib()
+    per_conf = lambda t: L.mlp_energy_workspace_bytes(t._dev()._h, 1, _lib.TERM_ALL, 1)
+    assert per_conf(tpe_def) < 80 << 20                                   # banded: <= 64 MB of partial forces
+    monkeypatch.setenv("MLP_NB_BANDS", "0")
+    if schedule == "whole list":
+        monkeypatch.setenv("MLP_NB_BLOCKS", "0")
     g = load_golden_murd_bbcb()
     tinfo, _ = tile_system(g[0], g[1], 24, batch=1, noise=0.2, seed=9)
     tpe = TorchProteinEnergy(None, tinfo, device=dev)
     assert tpe._dev().info()["nb_tile_pairs"] > 65535
-    got, want, g1, wg = _check_51k(tpe, topo, x, dev, [TOL] * 4, "md-like, one warp per tile pair")
+    assert (per_conf(tpe) > 200 << 20) == (schedule == "whole list")
+    got, want, g1, wg = _check_51k(tpe, topo, x, dev, [TOL] * 4, "md-like, " + schedule)
     assert rel(g1, wg.sum(0)) < TOL
-    got2, _, g2, _ = _check_51k(tpe_blk, topo, x, dev, [TOL] * 4, "md-like, block items")
+    got2, _, g2, _ = _check_51k(tpe_def, topo, x, dev, [TOL] * 4, "md-like, row bands")
     assert abs(got[3] - got2[3]) <= 1e-6 * abs(got2[3]) and rel(g1, g2) < 1e-6
 
 
