@@ -2458,8 +2458,10 @@ struct Workspace { size_t e_bonded, e_nb, fpart, total; };
 // prologue), but it needs 3 KB of partial forces per tile pair and conformation.  Two bounds keep that scratch O(N):
 //   * a batch is evaluated in chunks of conformations whose partial forces fit NB_WS_CAP_MB (MLP_NB_WS_MB; each chunk is
 //     one pair launch + one reduction, and a chunk of one 10 k-atom conformation is already 1.5 waves of warps);
-//   * when ONE conformation needs more than NB_BLK_MEM_MB (systems beyond ~26 k atoms) the block items are used: rows in
-//     registers, column forces accumulated in shared memory, about a fifth of the scratch.
+//   * when ONE conformation needs more than NB_BLK_MEM_MB (systems beyond ~26 k atoms) the tile-pair list is walked in
+//     row bands of at most that size (pair launch + reduction per band, the later bands adding to the gradient), or,
+//     with MLP_NB_BANDS=0, as block items: rows in registers, column forces accumulated in shared memory, about a
+//     fifth of the scratch, 2 % slower.
 // A pure function of the handle and the batch size: mlp_energy_workspace_bytes and mlp_energy_eval agree on it.
 #ifndef NB_BLK_MIN_ITEMS
 #define NB_BLK_MIN_ITEMS 8
