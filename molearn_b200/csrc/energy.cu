@@ -820,11 +820,14 @@ nb_kernel(const float* __restrict__ x, long sxb, long sxc, long sxn, const float
 
 // ---- packed-FP32 variant -------------------------------------------------------------------------------
 // Blackwell's FMA pipe executes fma/mul/add.f32x2 (SASS FFMA2/FMUL2/FADD2): two FP32 lanes per instruction at
-// the same flop rate, i.e. half the issue slots.  The scalar kernel above is issue-bound (79 % issue, 63 % FMA
-// pipe), so here every FMA-pipe operation of the pair term is packed over two j-atoms: j data sit in shared
-// memory component-wise (x[128], y[128], ...), a lane reads float4s = two (j, j+1) pairs per component; the
-// lane's i-atoms are kept duplicated (v, v) in registers; i-force accumulators are (even-j, odd-j) partial
+// the same flop rate.  The scalar kernel above is issue-bound (79 % issue, 63 % FMA pipe), so here every FMA-pipe
+// operation of the pair term is packed over two j-atoms: j data sit in shared memory component-wise (x[128],
+// y[128], ...), a lane reads float4s = two (j, j+1) pairs per component; the lane's i-atoms enter as 32-bit
+// broadcast operands (the compiler keeps one register per value); i-force accumulators are (even-j, odd-j) partial
 // sums folded at the end of the item.  Same arithmetic per pair as nb_pair_fast.
+// What the instructions cost on sm_100a (tools/micro/issue_bench.cu, operand_bench.cu): a packed
+// operation holds the pipe for two cycles - three when it reads three distinct register pairs -, and every MUFU / FMNMX /
+// IADD3 / SHFL between two of them costs roughly one more (LDS: none).  The loop is bound by 2 * packed + others.
 // NB_WFORM (repulsive mode only): the Lennard-Jones pair parameters are folded into one length,
 //   12 eps_ij (R_ij/d)^12 = (w_ij/d)^12,  w_ij = (12 eps_ij)^(1/12) R_ij = a_i b_j + b_i a_j,
 //   b = (12 eps)^(1/24), a = b R/2   (eps_ij = sqrt(eps_i eps_j), R_ij = R_i/2 + R_j/2; utils.py:814-815),
