@@ -159,6 +159,7 @@ struct mlp_energy {
     std::vector<PairBand> bands;
     int4* d_pairs_b = nullptr;     // the pair list ordered band by band (longest first inside a band)
     int band_max = 0;              // most pairs in a band
+    size_t band_bytes = 0;         // partial forces of one conformation per band (NB_BLK_MEM_MB; MLP_NB_BAND_KB)
     int band_mode = -1;            // MLP_NB_BANDS: -1 auto, 0 never (block items instead)
     int* d_red_off = nullptr;      // [n_nbt+1] per tile: range in d_red_list
     int* d_red_list = nullptr;     // entries pair*2 + side (0: the tile is the pair's I, 1: its J)
@@ -2351,8 +2352,10 @@ int pack_nonbonded(mlp_energy* E, const mlp_topology& T) {
     }
     // ---- row bands (large systems): at most NB_BLK_MEM_MB of partial forces per conformation and launch ----
     E->bands.clear(); E->band_max = 0;
-    if ((size_t)E->n_pairs * 6 * NB_T * sizeof(float) > ((size_t)NB_BLK_MEM_MB << 20)) {
-        const size_t cap = ((size_t)NB_BLK_MEM_MB << 20) / (6 * NB_T * sizeof(float));
+    E->band_bytes = (size_t)NB_BLK_MEM_MB << 20;
+    if (const char* env = std::getenv("MLP_NB_BAND_KB")) E->band_bytes = (size_t)std::max(3, std::atoi(env)) << 10;   // test hook: bands on small systems
+    if ((size_t)E->n_pairs * 6 * NB_T * sizeof(float) > E->band_bytes) {
+        const size_t cap = E->band_bytes / (6 * NB_T * sizeof(float));
         std::vector<int4> pairs_b;
         int I0 = 0;
         while (I0 < nt) {
@@ -2481,7 +2484,7 @@ int block_level(const mlp_energy* e, int64_t B) {   // -1: one warp per tile pai
         for (int lv = 0; lv < NB_BLK_LEVELS; ++lv) if (NB_BLK_ROWS[lv] == e->blk_mode) return lv;
         return NB_BLK_LEVELS - 1;
     }
-    if ((size_t)e->n_pairs * 6 * NB_T * sizeof(float) <= ((size_t)NB_BLK_MEM_MB << 20)) return -1;
+    if ((size_t)e->n_pairs * 6 * NB_T * sizeof(float) <= e->band_bytes) return -1;
     if (e->band_mode != 0 && !e->bands.empty()) return -1;       // the tile-pair kernel, band by band
     // memory-bound regime: the biggest blocks that still leave every resident warp slot NB_BLK_MIN_ITEMS items, at least 4 rows
     const bool tab = e->lut_on && e->nb_mode != MLP_NB_FULL;

@@ -402,7 +402,7 @@ def test_conformation_extent_limit_is_reported(dev, energy_objs, golden_energy):
 
 
 @pytest.mark.parametrize("knob", ["MLP_NB_PACKED=0", "MLP_NO_OVERLAP=1", "MLP_BONDED_TILE=64", "MLP_BONDED_TILE=40", "MLP_NB_BLOCKS=8", "MLP_NB_BLOCKS=2",
-                                  "MLP_NB_FIRST=1", "MLP_NB_LUT=0", "MLP_NB_WS_MB=1"])
+                                  "MLP_NB_FIRST=1", "MLP_NB_LUT=0", "MLP_NB_WS_MB=1", "MLP_NB_BAND_KB=96"])
 def test_alternative_code_paths_agree(knob, dev, golden_topo, golden_energy, monkeypatch):
     """The library's run-time switches (read when a handle is created) select other code paths of the same maths: the
     scalar pair kernel, no side-stream overlap, smaller bonded tiles (other work-item matchings and halos).  Each must
@@ -418,6 +418,10 @@ def test_alternative_code_paths_agree(knob, dev, golden_topo, golden_energy, mon
     en = golden_energy("bbcb")
     gf = list(en["grad_frames"])
     x = torch.from_numpy(en["x"][gf]).to(dev).permute(0, 2, 1)
+    if name == "MLP_NB_BAND_KB":    # 96 KB = 32 tile pairs per band: the 170 tile pairs of MurD in six row bands (the schedule of large systems)
+        dv, n0 = tpe._dev(), tpe._dev().launches
+        dv.eval(x, torch.empty(len(gf), 4, device=dev), torch.empty_like(x), None, _lib.TERM_ALL)
+        assert dv.launches - n0 > 1 + 2 * 4                            # bonded + (pair, reduction) per band
     if name == "MLP_NB_WS_MB":      # 1 MB of partial forces = one conformation per pair launch: a chunked batch
         dv, n0 = tpe._dev(), tpe._dev().launches
         dv.eval(x, torch.empty(len(gf), 4, device=dev), torch.empty_like(x), None, _lib.TERM_ALL)
