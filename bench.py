@@ -826,7 +826,8 @@ def main():
     # streams 400 k conformations/s - consecutive batches overlap like the two-stream device-resident mode).  The host
     # reads every batch's results (result(k) waits for batch k).
     from molearn_b200.loss_functions import GraphedEnergyStep
-    gstep = GraphedEnergyStep(tpe, hx, n_streams=int(os.environ.get("MLP_GRAPH_STREAMS", 12)))
+    prio = int(os.environ.get("MLP_GRAPH_PRIORITIES", 2))     # two stream priority levels: steady rate from the first batches on (see GraphedEnergyStep)
+    gstep = GraphedEnergyStep(tpe, hx, n_streams=int(os.environ.get("MLP_GRAPH_STREAMS", 12)), priority_levels=prio)
     n_slots = len(hx)
 
     def timed_graph(steps, warm):
@@ -861,7 +862,7 @@ def main():
     # the same loop with the gradient left on the device (a consumer on the GPU, e.g. the decoder's backward pass):
     # H2D of every batch and D2H of its energies only - half the PCIe / host-memory traffic
     gstep_full = gstep
-    gstep = GraphedEnergyStep(tpe, hx, n_streams=len(gstep_full.streams), gradient_to_host=False)
+    gstep = GraphedEnergyStep(tpe, hx, n_streams=len(gstep_full.streams), gradient_to_host=False, priority_levels=prio)
     ms_graph_dev, _ = timed_graph(args.steps, 2 * n_slots)
     gstep = gstep_full
     # parity of the replayed step with the eager call on the same host batch (bit for bit)
@@ -876,7 +877,7 @@ def main():
     e2e = {"value": world * B * args.steps / (ms_graph * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": per, "d2h_bytes_per_step": per + B * 16, "ms_per_step": ms_graph / args.steps,
            "mode": "GraphedEnergyStep: H2D + energy_per_conformation + backward + D2H of energies and gradient captured once per pinned "
-                   "host buffer through the public autograd path, one CUDA-graph replay per batch, " + f"{n_slots} pinned buffers over {len(gstep.streams)} streams (consecutive batches overlap on the GPU like the two_streams mode); the host reads every result",
+                   "host buffer through the public autograd path, one CUDA-graph replay per batch, " + f"{n_slots} pinned buffers over {len(gstep.streams)} streams with {prio} priority levels (consecutive batches overlap on the GPU like the two_streams mode); the host reads every result",
            "graph_equals_eager": graph_equal,
            "gradient_on_device": {"value": world * B * args.steps / (ms_graph_dev * 1e-3), "ms_per_step": ms_graph_dev / args.steps,
                                   "h2d_bytes_per_step": per, "d2h_bytes_per_step": B * 16,

@@ -26,7 +26,7 @@ from .torch_protein_energy import TorchProteinEnergy
 
 class GraphedEnergyStep:
     def __init__(self, energy: TorchProteinEnergy, host_batches, nonbonded: bool = True, n_streams: int = 2,
-                 gradient_to_host: bool = True):
+                 gradient_to_host: bool = True, priority_levels: int = 0):
         """``gradient_to_host=False`` keeps dE/dx on the device (``result`` then returns the device tensor): the case of
         a consumer that lives on the GPU, e.g. a decoder's backward pass - only the energies [B,4] cross PCIe."""
         self.gradient_to_host = gradient_to_host
@@ -34,7 +34,13 @@ class GraphedEnergyStep:
             raise ValueError("GraphedEnergyStep needs at least one pinned host buffer")
         self.energy = energy
         dev = energy.device
-        self.streams = [torch.cuda.Stream(dev) for _ in range(max(1, n_streams))]
+        # priority_levels = L > 1: the streams get L descending priority levels in turn.  Batches submitted together are
+        # otherwise served interleaved and finish all at once (their read-backs then arrive in a burst and the host
+        # re-submits in a burst); with two levels half of them are served first - a short run reaches its steady rate
+        # at once (390 k instead of 358 k conformations/s over 20 batches of MurD x 64; the long-run rate of the loop with
+        # the gradient read-back drops from 427 k to 396 k, the one with the gradient on the device rises to 438 k).
+        lev = int(priority_levels)
+        self.streams = [torch.cuda.Stream(dev, priority=(-(lev - 1) + (j % lev)) if lev > 1 else 0) for j in range(max(1, n_streams))]
         self.slots = []
         for k, hx in enumerate(host_batches):
             if hx.is_cuda or hx.dtype != torch.float32 or hx.dim() != 3 or hx.shape[1:] != (energy.n_atoms, 3):
