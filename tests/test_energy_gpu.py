@@ -639,5 +639,16 @@ def test_graphed_step_equals_eager(dev, energy_objs, golden_energy):
             assert torch.equal(e, ee.detach().cpu()) and torch.equal(g, xe.grad.permute(0, 2, 1).cpu()), (rep, k)
         bufs[1].add_(0.01)                                              # the loader writes new batches into the same pinned buffers
         bufs[2].mul_(1.001)
+    # dE/dx left on the device (a consumer on the GPU), three streams with two priority levels: the same numbers
+    step2 = GraphedEnergyStep(tpe, bufs, n_streams=3, gradient_to_host=False, priority_levels=2)
+    for k in range(3):
+        step2.submit(k)
+    for k in range(3):
+        e, g = step2.result(k)
+        assert g.is_cuda and not e.is_cuda
+        step.submit(k)
+        e1, g1 = step.result(k)
+        step2.synchronize()
+        assert torch.equal(e, e1) and torch.equal(g.cpu(), g1), k
     with pytest.raises(ValueError):
         GraphedEnergyStep(tpe, [x0])                                    # not pinned
