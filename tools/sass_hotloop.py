@@ -17,6 +17,8 @@ def packed(b):
 
 
 hot = min((b for b in blocks if packed(b) >= 150), key=len)      # the masked variant of the same step carries 48 more selects
+while hot and hot[0][1].startswith("CS2R"):                      # zeroing of the j-force accumulators in front of the loop
+    hot = hot[1:]
 cnt = collections.Counter(t.split()[0].split(".")[0] for _, t in hot)
 pk = cnt["FFMA2"] + cnt["FMUL2"] + cnt["FADD2"]
 n, hist, cyc, _ = analyse(hot)
